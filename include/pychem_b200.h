@@ -1,0 +1,134 @@
+/*
+ * pychem_b200.h -- C ABI of the B200-native replacement for pychem's two-electron hot path.
+ *
+ * Plain C, caller-owned buffers, no torch/numpy types.  Every function returns 0 on success and
+ * a non-zero code otherwise; pc_last_error() then describes the failure (CUDA error string or
+ * argument problem).  Nothing here ever calls exit().  Buffers documented "host or device" are
+ * classified with cudaPointerGetAttributes, so a torch tensor's data_ptr() can be passed as is.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * checkout).  The reference's eleven fine-grained `_c_ints` functions (Methods/_c_ints.c:68-81)
+ * are per-recursion-step micro-calls driven from Python; this ABI replaces their CALLERS
+ * (SURVEY.md section 8(b)), which is where >90 % of the reference's time goes.
+ */
+#ifndef PYCHEM_B200_H
+#define PYCHEM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pc_basis pc_basis; /* opaque: shell table, shell-pair tables, Boys table, plans */
+
+/* digestion variants for pc_jk_* (what make_coulomb_exchange_matrices is asked to do) */
+#define PC_JK_RHF 2 /* symmetric densities, D_alpha == D_beta (one exchange matrix computed)      */
+#define PC_JK_UHF 3 /* symmetric densities, two spins                                             */
+#define PC_JK_GEN 4 /* general non-symmetric densities (NOCI co-densities, Methods/noci.py:204-211) */
+
+/* Last error message of the calling thread ("" if none). */
+const char* pc_last_error(void);
+
+/* Number of visible CUDA devices; fails (non-zero) when there is no usable device. */
+int pc_device_count(int* count);
+
+/*
+ * Build the device-resident basis from a flat shell table.
+ *   Replaces: ContractedGaussian constants (Util/structures.py:834-856), the eager ShellPair
+ *   construction (Util/structures.py:510-523, 918-956) and _c_ints.shellpair_quantities
+ *   (Methods/_c_ints.c:120-155, Methods/c_ints/shellpair_quantities.c:5-38).
+ *   l[s] <= 2 (s, p, d); d shells must be spherical (is_cart[s] == 0) in this build.
+ *   scc = cc*(2a)^((l+1.5)/2) (Util/structures.py:843); first_fn = index of the shell's first
+ *   basis function (atoms -> shells -> functions, Util/structures.py:511-520).
+ */
+int pc_basis_create(int device, int nshell, const int* l, const int* K, const int* is_cart,
+                    const int* first_fn, const double* centres /*[nshell][3] bohr*/,
+                    const double* exps, const double* scc, pc_basis** out);
+int pc_basis_destroy(pc_basis* h);
+int pc_basis_nbf(const pc_basis* h, int* nbf);
+/* cudaStream_t the handle launches on (for CUDA-event timing on the launching stream). */
+int pc_basis_stream(const pc_basis* h, void** stream);
+
+/*
+ * Schwarz factors.  Replaces pass 1 of hartree_fock.evaluate_2e_ints
+ * (Methods/hartree_fock.py:244-254): bounds[p][m*nfb+n] = sqrt((mn|mn)) for shell pair p=(a<=b)
+ * in upper-triangular order p = a*nshell - a(a-1)/2 + (b-a); pmax[p] = max over the block.
+ * Both outputs are host buffers (bounds: npair*49 doubles, pmax: npair doubles; either may be
+ * NULL).  Must be called before any screened entry point; sorts the pair tables by pmax.
+ */
+int pc_schwarz(pc_basis* h, double* bounds, double* pmax);
+
+/*
+ * Build the screened, class-bucketed shell-quartet schedule.
+ *   Replaces the loop nest + screen of pass 2 (Methods/hartree_fock.py:276-295): a unique
+ *   quartet (ab|cd) survives iff max(B_ab)*max(B_cd) > thresh (strict), diagonal quartets
+ *   (ab|ab) always do.  Within every (bra bucket, ket bucket) the task range is cut into
+ *   nranks equal contiguous slices (cost is uniform inside a bucket pair) and this handle keeps
+ *   slice `rank` -- the static cost-balanced multi-GPU partition.
+ *   Outputs (may be NULL): quartets/eris kept by this rank, and in total.
+ */
+int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quartets,
+            long long* my_eris, long long* all_quartets, long long* all_eris);
+
+/*
+ * Arbitrary shell quartets, for parity tests: out receives, for quartet q, the block
+ * (nfa, nfb, nfc, nfd) in C order starting at out[offsets[q]] -- exactly what
+ * integrals.two_electron(shell_pair1, shell_pair2, 0, -1.0) returns
+ * (Methods/integrals.py:427-555).  abcd = [n][4] shell indices with a<=b, c<=d.  Host buffers.
+ */
+int pc_eri_quartets(pc_basis* h, int n, const int* abcd, const long long* offsets, double* out);
+
+/*
+ * Dense tensor G[N][N][N][N] (C order) with the reference's screening and 8-fold scatter.
+ *   Replaces hartree_fock.evaluate_2e_ints pass 2 + the scatter loops
+ *   (Methods/hartree_fock.py:266-273, 314-325).  Needs pc_schwarz + pc_plan(rank 0 of 1).
+ *   G_dev: device buffer of N^4 doubles (zeroed here); G_host (may be NULL) receives a copy.
+ */
+int pc_eri_tensor(pc_basis* h, double* G_dev, double* G_host);
+
+/*
+ * J/K from the stored tensor: one streaming pass over G (HBM-bound).
+ *   Replaces the three einsums of hartree_fock.make_coulomb_exchange_matrices
+ *   (Methods/hartree_fock.py:345-347): J = einsum("cd,abcd->ab", Dt, G),
+ *   Xa = einsum("cb,abcd->ad", -Da, G), Xb likewise (Exchange carries the minus sign).
+ *   Dt/Da/Db/J/Xa/Xb: N*N doubles each, host or device.  Densities may be non-symmetric.
+ */
+int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const double* Da,
+                 const double* Db, double* J, double* Xa, double* Xb);
+
+/*
+ * Integral-direct J/K: ERIs of this rank's slice of the plan are regenerated and digested on
+ * the fly (no N^4 store).  Same outputs as pc_jk_stored.  variant = PC_JK_RHF/UHF/GEN.
+ *   pc_jk_direct_accumulate: acc_dev = device buffer of 3*N*N doubles (zeroed here) receiving
+ *     this rank's partial half-accumulators [J | Ka | Kb]; sum it over ranks (NCCL all-reduce),
+ *   pc_jk_finalize: turns the summed accumulators into J, Xa, Xb (symmetrisation and sign).
+ *   pc_jk_direct: both steps on one GPU with an internal accumulator.
+ */
+int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const double* Da,
+                            const double* Db, double* acc_dev);
+int pc_jk_finalize(pc_basis* h, int variant, const double* acc_dev, double* J, double* Xa,
+                   double* Xb);
+int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
+                 double* J, double* Xa, double* Xb);
+
+/*
+ * Measurement hooks (bench.py): with profiling on, pc_jk_direct_accumulate brackets every plan
+ * item (one kernel launch per (bra bucket, ket bucket)) with CUDA events on the launching stream
+ * and synchronises at the end.  pc_plan_items reports, per item k: cls[4k..] = (lx1,ly1,lx2,ly2),
+ * kprim[2k..] = primitive pairs per bra/ket shell pair, tasks[2k..] = (all quartets, this rank's
+ * quartets), ms[k] = device time of the item in the last profiled accumulate.  Arrays may be NULL.
+ */
+int pc_set_profiling(pc_basis* h, int on);
+int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim,
+                  long long* tasks, float* ms);
+
+/* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int pc_launch_count(const pc_basis* h, long long* n);
+
+/* Register-resident DFMA micro-benchmark: measured FP64 FMA peak of `device` in TFLOP/s
+ * (the roofline denominator for the ERI kernels; MEASURED_PEAKS.json has no FP64 entry). */
+int pc_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCHEM_B200_H */

@@ -1,0 +1,215 @@
+"""Thin Python owner of a `pc_basis` handle (include/pychem_b200.h).
+
+PyTorch is used for two things only: owning device buffers (the dense tensor, the J/K
+accumulators) and the NCCL all-reduce of the partial J/K accumulators over ranks.
+All arithmetic happens in the CUDA library behind the C ABI.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .basis_table import BasisTable
+
+RHF, UHF, GEN = 2, 3, 4           # PC_JK_* in include/pychem_b200.h
+INTEGRAL_THRESHOLD = 1.0e-8        # Data/constants.py:31
+
+
+def _ptr(x):
+    """void* of a numpy array (host) or a torch tensor (device/host)."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        if x.dtype != np.float64 or not x.flags["C_CONTIGUOUS"]:
+            raise TypeError("expected a C-contiguous float64 array")
+        return ctypes.c_void_p(x.ctypes.data)
+    return ctypes.c_void_p(x.data_ptr())        # torch.Tensor
+
+
+def _as_f64(x):
+    if isinstance(x, np.ndarray):
+        return np.ascontiguousarray(x, dtype=np.float64)
+    if hasattr(x, "data_ptr"):
+        import torch
+        if x.dtype != torch.float64 or not x.is_contiguous():
+            raise TypeError("expected a contiguous float64 tensor")
+        return x
+    return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def classify_densities(Dt, Da, Db, tol=0.0):
+    """Pick the cheapest exact digestion variant for these densities."""
+    Dt, Da, Db = (np.asarray(x) for x in (Dt, Da, Db))
+    sym = all(np.array_equal(x, x.T) for x in (Dt, Da, Db))
+    if not sym:
+        return GEN
+    return RHF if np.array_equal(Da, Db) else UHF
+
+
+class DeviceBasis:
+    """Device-resident basis + shell-pair tables + screened quartet plan for one molecule."""
+
+    def __init__(self, molecule_or_table, device=None):
+        self.table = (molecule_or_table if isinstance(molecule_or_table, BasisTable)
+                      else BasisTable(molecule_or_table))
+        self.lib = _lib.load()
+        if device is None:
+            import torch
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        self.device = int(device)
+        t = self.table
+        h = ctypes.c_void_p()
+        ip = lambda a: a.ctypes.data_as(_lib.c_ip)      # noqa: E731
+        dp = lambda a: a.ctypes.data_as(_lib.c_dp)      # noqa: E731
+        _lib.check(self.lib.pc_basis_create(self.device, t.nshell, ip(t.l), ip(t.K), ip(t.is_cart),
+                                            ip(t.first_fn), dp(t.centres), dp(t.exps), dp(t.scc),
+                                            ctypes.byref(h)))
+        self.h = h
+        self.nbf = t.nbf
+        self.nshell = t.nshell
+        self.npair = t.nshell * (t.nshell + 1) // 2
+        self.counts = None
+        self._acc = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pc_basis_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ plumbing
+    def stream_ptr(self):
+        s = ctypes.c_void_p()
+        _lib.check(self.lib.pc_basis_stream(self.h, ctypes.byref(s)))
+        return s.value
+
+    def torch_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(self.stream_ptr(), device=self.device)
+
+    def launch_count(self):
+        n = ctypes.c_longlong()
+        _lib.check(self.lib.pc_launch_count(self.h, ctypes.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ Schwarz + plan
+    def schwarz(self):
+        """(bounds[npair,49], pmax[npair]); hartree_fock.py:244-254."""
+        bounds = np.zeros((self.npair, 49))
+        pmax = np.zeros(self.npair)
+        _lib.check(self.lib.pc_schwarz(self.h, bounds.ctypes.data_as(_lib.c_dp),
+                                       pmax.ctypes.data_as(_lib.c_dp)))
+        return bounds, pmax
+
+    def plan(self, thresh=INTEGRAL_THRESHOLD, rank=0, nranks=1):
+        v = [ctypes.c_longlong() for _ in range(4)]
+        _lib.check(self.lib.pc_plan(self.h, float(thresh), int(rank), int(nranks),
+                                    *[ctypes.byref(x) for x in v]))
+        self.counts = dict(my_quartets=v[0].value, my_eris=v[1].value,
+                           all_quartets=v[2].value, all_eris=v[3].value,
+                           thresh=float(thresh), rank=rank, nranks=nranks)
+        return self.counts
+
+    def set_profiling(self, on):
+        _lib.check(self.lib.pc_set_profiling(self.h, int(bool(on))))
+
+    def plan_items(self):
+        """Per (bra bucket, ket bucket) launch: class, contraction depths, task counts and the
+        device time of the last profiled accumulate."""
+        n = ctypes.c_int()
+        _lib.check(self.lib.pc_plan_items(self.h, 0, ctypes.byref(n), None, None, None, None))
+        m = n.value
+        cls = np.zeros((m, 4), dtype=np.int32)
+        kprim = np.zeros((m, 2), dtype=np.int32)
+        tasks = np.zeros((m, 2), dtype=np.int64)
+        ms = np.zeros(m, dtype=np.float32)
+        _lib.check(self.lib.pc_plan_items(self.h, m, ctypes.byref(n), cls.ctypes.data_as(_lib.c_ip),
+                                          kprim.ctypes.data_as(_lib.c_ip),
+                                          tasks.ctypes.data_as(_lib.c_llp),
+                                          ms.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+        return cls, kprim, tasks, ms
+
+    # ------------------------------------------------------------------ ERIs
+    def eri_quartets(self, quartets):
+        """Blocks (nfa,nfb,nfc,nfd) for shell quartets [(a,b,c,d)], a<=b, c<=d."""
+        q = np.ascontiguousarray(np.asarray(quartets, dtype=np.int32).reshape(-1, 4))
+        nfn = self.table.nfn
+        sizes = [int(nfn[a] * nfn[b] * nfn[c] * nfn[d]) for a, b, c, d in q]
+        offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        out = np.zeros(int(offs[-1]))
+        _lib.check(self.lib.pc_eri_quartets(self.h, len(q), q.ctypes.data_as(_lib.c_ip),
+                                            offs.ctypes.data_as(_lib.c_llp),
+                                            out.ctypes.data_as(_lib.c_dp)))
+        return [out[offs[k]:offs[k + 1]].reshape(nfn[a], nfn[b], nfn[c], nfn[d])
+                for k, (a, b, c, d) in enumerate(q)]
+
+    def eri_tensor(self, thresh=INTEGRAL_THRESHOLD, to_host=True):
+        """Dense (N,N,N,N) tensor on the device (torch tensor) and optionally a host copy."""
+        import torch
+        self.plan(thresh, 0, 1)
+        N = self.nbf
+        G_dev = torch.empty((N, N, N, N), dtype=torch.float64, device="cuda:%d" % self.device)
+        G_host = np.empty((N, N, N, N)) if to_host else None
+        _lib.check(self.lib.pc_eri_tensor(self.h, _ptr(G_dev), _ptr(G_host)))
+        return G_dev, G_host
+
+    # ------------------------------------------------------------------ J/K
+    def _outputs(self, like):
+        N = self.nbf
+        if isinstance(like, np.ndarray):
+            return [np.empty((N, N)) for _ in range(3)]
+        import torch
+        return [torch.empty((N, N), dtype=torch.float64, device=like.device) for _ in range(3)]
+
+    def jk_stored(self, G_dev, Dt, Da, Db):
+        Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
+        J, Xa, Xb = self._outputs(Dt)
+        _lib.check(self.lib.pc_jk_stored(self.h, _ptr(G_dev), _ptr(Dt), _ptr(Da), _ptr(Db),
+                                         _ptr(J), _ptr(Xa), _ptr(Xb)))
+        return J, Xa, Xb
+
+    def accumulator(self):
+        import torch
+        if self._acc is None:
+            self._acc = torch.empty(3 * self.nbf * self.nbf, dtype=torch.float64,
+                                    device="cuda:%d" % self.device)
+        return self._acc
+
+    def jk_direct(self, Dt, Da, Db, variant=None, group=None):
+        """Integral-direct J/K.  With an initialised torch.distributed process group and a plan
+        built with nranks>1, partial accumulators are summed with one NCCL all-reduce."""
+        Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
+        if variant is None:
+            variant = classify_densities(Dt, Da, Db) if isinstance(Dt, np.ndarray) else GEN
+        if self.counts is None:
+            self.plan()
+        J, Xa, Xb = self._outputs(Dt)
+        if self.counts["nranks"] == 1:
+            _lib.check(self.lib.pc_jk_direct(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db),
+                                             _ptr(J), _ptr(Xa), _ptr(Xb)))
+            return J, Xa, Xb
+        import torch
+        import torch.distributed as dist
+        acc = self.accumulator()
+        _lib.check(self.lib.pc_jk_direct_accumulate(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db), _ptr(acc)))
+        # the library launched on its own stream: order the collective after it
+        ev = torch.cuda.Event()
+        ev.record(self.torch_stream())
+        torch.cuda.current_stream().wait_event(ev)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        ev2 = torch.cuda.Event()
+        ev2.record(torch.cuda.current_stream())
+        self.torch_stream().wait_event(ev2)
+        _lib.check(self.lib.pc_jk_finalize(self.h, variant, _ptr(acc), _ptr(J), _ptr(Xa), _ptr(Xb)))
+        return J, Xa, Xb
+
+
+def fp64_peak_tflops(device=0):
+    v = ctypes.c_double()
+    _lib.check(_lib.load().pc_fp64_peak(int(device), ctypes.byref(v)))
+    return v.value

@@ -1,0 +1,105 @@
+"""GPU-backed mirrors of the two hot functions of the reference's Methods/hartree_fock.py.
+
+    evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0)      (hartree_fock.py:241-325)
+    make_coulomb_exchange_matrices(molecule, this)                 (hartree_fock.py:329-347)
+
+Same names, arguments and attribute side effects, so the reference's SCF driver
+(hartree_fock.do), NOCI (noci.py:247,275,291) and MP2 (mp2.py:46) run unchanged once
+``install()`` has rebound the two names in the reference's module:
+
+  * ``molecule.Bounds[a][b]``   per-function Schwarz factors sqrt((mn|mn))      (:249-254)
+  * ``molecule.CoulombIntegrals`` dense (N,N,N,N) ndarray incl. screening zeros   (:266-325)
+  * ``this.Total.Coulomb``, ``this.Alpha.Exchange``, ``this.Beta.Exchange`` fresh N x N arrays,
+    Exchange carrying the minus sign, for possibly non-symmetric densities        (:345-347)
+
+Two modes, chosen per molecule (override with the environment variable PYCHEM_B200_MODE=
+stored|direct, no new input keyword is needed):
+  stored  N^4 fits the budget: the tensor lives in HBM, J/K is one streaming pass over it.
+  direct  otherwise: ERIs are regenerated and digested on the fly every Fock build;
+          ``molecule.CoulombIntegrals`` is then left as None (mp2/properties need `stored`).
+There is no CPU fallback: without a CUDA device / the built library these functions raise.
+"""
+import os
+
+import numpy as np
+
+from . import engine
+from .integrals import device_basis
+
+STORED_LIMIT_BYTES = int(float(os.environ.get("PYCHEM_B200_STORED_LIMIT_GB", "24")) * 2 ** 30)
+
+_STATE = {}     # id(molecule) -> dict(mode=..., G_dev=..., db=...)
+
+
+def _mode_for(molecule):
+    forced = os.environ.get("PYCHEM_B200_MODE", "").lower()
+    if forced in ("stored", "direct"):
+        return forced
+    return "stored" if 8 * int(molecule.NOrbitals) ** 4 <= STORED_LIMIT_BYTES else "direct"
+
+
+def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
+    if ints_type != 0:
+        raise NotImplementedError("scattering integrals (ints_type=1) are not part of the GPU path")
+    db = device_basis(molecule)
+    table = db.table
+    bounds, _ = db.schwarz()
+    if not isinstance(molecule.Bounds, list) or len(molecule.Bounds) != table.nshell:
+        molecule.Bounds = [[0.0] * table.nshell for _ in range(table.nshell)]
+    p = 0
+    for a in range(table.nshell):
+        na = int(table.nfn[a])
+        for b in range(a, table.nshell):
+            nb = int(table.nfn[b])
+            molecule.Bounds[a][b] = bounds[p, :na * nb].reshape(na, nb).copy()
+            p += 1
+    mode = _mode_for(molecule)
+    st = {"mode": mode, "db": db, "G_dev": None, "molecule": molecule}
+    if mode == "stored":
+        G_dev, G_host = db.eri_tensor(engine.INTEGRAL_THRESHOLD, to_host=True)
+        st["G_dev"] = G_dev
+        molecule.CoulombIntegrals = G_host
+    else:
+        db.plan(engine.INTEGRAL_THRESHOLD, 0, 1)
+        molecule.CoulombIntegrals = None
+    _STATE[id(molecule)] = st
+
+
+def make_coulomb_exchange_matrices(molecule, this):
+    st = _STATE.get(id(molecule))
+    if st is None or st["molecule"] is not molecule or st["db"].h is None:
+        evaluate_2e_ints(molecule)
+        st = _STATE[id(molecule)]
+    db = st["db"]
+    Dt = np.ascontiguousarray(this.Total.Density, dtype=np.float64)
+    Da = np.ascontiguousarray(this.Alpha.Density, dtype=np.float64)
+    Db = np.ascontiguousarray(this.Beta.Density, dtype=np.float64)
+    if st["mode"] == "stored":
+        J, Xa, Xb = db.jk_stored(st["G_dev"], Dt, Da, Db)
+    else:
+        J, Xa, Xb = db.jk_direct(Dt, Da, Db)
+    this.Total.Coulomb = J
+    this.Alpha.Exchange = Xa
+    this.Beta.Exchange = Xb
+
+
+def install(reference_hartree_fock, reference_noci=None):
+    """Rebind the two hot functions inside the reference's own modules (the drop-in).
+
+    ``reference_hartree_fock`` is the reference's ``Methods.hartree_fock`` module;
+    noci.py calls ``hf.make_coulomb_exchange_matrices`` through that module object, so
+    rebinding there covers NOCI as well.  Returns a callable that undoes the patch."""
+    saved = (reference_hartree_fock.evaluate_2e_ints,
+             reference_hartree_fock.make_coulomb_exchange_matrices)
+    reference_hartree_fock.evaluate_2e_ints = evaluate_2e_ints
+    reference_hartree_fock.make_coulomb_exchange_matrices = make_coulomb_exchange_matrices
+
+    def uninstall():
+        reference_hartree_fock.evaluate_2e_ints, reference_hartree_fock.make_coulomb_exchange_matrices = saved
+    return uninstall
+
+
+def release(molecule=None):
+    keys = list(_STATE) if molecule is None else [id(molecule)]
+    for k in keys:
+        _STATE.pop(k, None)

@@ -1,0 +1,80 @@
+"""GPU-backed mirror of the reference's two-electron entry point in Methods/integrals.py.
+
+    two_electron(shell_pair1, shell_pair2, ints_type, grid_value) -> ndarray(nlA, nlB, nlC, nlD)
+
+Same name, arguments and return convention as Methods/integrals.py:427-555 (including the
+block being returned in (pair1 | pair2) order whichever pair carries more angular momentum).
+The whole fundamentals -> VRR -> contraction -> HRR -> normalise -> spherical chain runs in one
+CUDA kernel launch behind the C ABI (pc_eri_quartets); no CPU fallback exists.
+
+``ints_type == 1`` (scattering fundamentals, Methods/c_ints/two_electron_scattering.c) is out
+of scope of this build and raises NotImplementedError.
+"""
+import numpy as np
+
+from .engine import DeviceBasis
+
+_BASIS_CACHE = {}
+
+
+def device_basis(molecule):
+    """One DeviceBasis per molecule object (rebuilt when the basis set was swapped,
+    cf. structures.update_basis, Util/structures.py:49-55)."""
+    key = id(molecule)
+    stamp = (getattr(molecule, "Basis", None), int(molecule.NCgtf), int(molecule.NOrbitals))
+    ent = _BASIS_CACHE.get(key)
+    if ent is None or ent[0] != stamp or ent[2] is not molecule:
+        if ent is not None:
+            ent[1].close()
+        ent = (stamp, DeviceBasis(molecule), molecule)
+        _BASIS_CACHE[key] = ent
+    return ent[1]
+
+
+def release(molecule=None):
+    """Free cached device state (all molecules when called without argument)."""
+    keys = list(_BASIS_CACHE) if molecule is None else [id(molecule)]
+    for k in keys:
+        ent = _BASIS_CACHE.pop(k, None)
+        if ent is not None:
+            ent[1].close()
+
+
+def shell_index_of(molecule, shell):
+    """Global shell index of a ``Shell`` (the reference keeps only the first basis-function
+    index list ``Ivec`` on it, Util/structures.py:962-968)."""
+    first = shell.Ivec[0]
+    table = device_basis(molecule).table
+    idx = int(np.searchsorted(table.first_fn, first))
+    if idx >= table.nshell or table.first_fn[idx] != first:
+        raise ValueError("shell does not belong to this molecule")
+    return idx
+
+
+def two_electron(shell_pair1, shell_pair2, ints_type=0, grid_value=-1.0, molecule=None):
+    """(ab|cd) block for two ShellPair objects.
+
+    ``molecule`` must be given (or have been bound with ``bind(molecule)``) so the shells can
+    be located in the device tables; the reference's signature has no such argument because
+    its ShellPair objects carry the primitive tables themselves.
+    """
+    if ints_type != 0:
+        raise NotImplementedError("scattering fundamentals (ints_type=1) are not part of the GPU path")
+    molecule = molecule or _BOUND.get("molecule")
+    if molecule is None:
+        raise ValueError("two_electron: bind a molecule first (pychem_b200.integrals.bind)")
+    db = device_basis(molecule)
+    a = shell_index_of(molecule, shell_pair1.Centre1)
+    b = shell_index_of(molecule, shell_pair1.Centre2)
+    c = shell_index_of(molecule, shell_pair2.Centre1)
+    d = shell_index_of(molecule, shell_pair2.Centre2)
+    return db.eri_quartets([(a, b, c, d)])[0]
+
+
+_BOUND = {}
+
+
+def bind(molecule):
+    """Make ``molecule`` the default for two_electron()."""
+    _BOUND["molecule"] = molecule
+    return device_basis(molecule)

@@ -1,0 +1,232 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(include/pychem_b200.h via pychem_b200.engine), against
+
+  * the golden vectors minted from the reference itself (tests/golden/, oracle/make_golden.py),
+  * the CPU oracle (oracle/eri_oracle.c) on seeded inputs it finishes in seconds,
+  * size-independent properties at the full BASELINE sizes (stored == direct, linearity,
+    symmetry, rank-partition additivity).
+
+Bars (north_star): individual ERIs within 1e-12 absolute (FP64, bit-exact is not defined for
+reordered floating-point sums); J/K within 1e-10 absolute; energies within 1e-8 Eh.
+"""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+ERI_TOL = 1.0e-12
+JK_TOL = 1.0e-10
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from pychem_b200 import engine
+    return engine
+
+
+def _basis(eng, name):
+    return eng.DeviceBasis(helpers.molecule(name))
+
+
+# --------------------------------------------------------------------------------------------
+# golden vectors from the reference
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,fixture", [("h2o2", "h2o2_631gss.npz"), ("benzene", "benzene_631gs.npz")])
+def test_sampled_quartets_all_21_classes(eng, gold, name, fixture):
+    g = gold(fixture)
+    db = _basis(eng, name)
+    blocks = db.eri_quartets(g["quartets"])
+    worst = 0.0
+    for blk, lo, hi in zip(blocks, g["offsets"][:-1], g["offsets"][1:]):
+        assert blk.size == hi - lo
+        worst = max(worst, float(np.abs(blk.ravel() - g["blocks"][lo:hi]).max()))
+    assert worst < ERI_TOL, worst
+    db.close()
+
+
+@pytest.mark.parametrize("name,fixture", [("h2", "h2_6311g.npz"), ("lih", "lih_631g.npz"),
+                                          ("h2o", "h2o_631gss.npz")])
+def test_dense_tensor_and_bounds(eng, gold, name, fixture):
+    g = gold(fixture)
+    db = _basis(eng, name)
+    bounds, pmax = db.schwarz()
+    assert np.abs(bounds - g["bounds"]).max() < 1e-12
+    G_dev, G = db.eri_tensor(1.0e-8, to_host=True)
+    assert G.shape == g["G"].shape
+    assert np.abs(G - g["G"]).max() < ERI_TOL
+    assert np.abs(G_dev.cpu().numpy() - G).max() == 0.0
+    db.close()
+
+
+@pytest.mark.parametrize("fixture,name,keys", [("h2_6311g.npz", "h2", ("",)), ("lih_631g.npz", "lih", ("",)),
+                                               ("h2o_631gss.npz", "h2o", ("", "2"))])
+def test_jk_stored_and_direct_vs_reference_einsum(eng, gold, fixture, name, keys):
+    g = gold(fixture)
+    db = _basis(eng, name)
+    db.schwarz()
+    G_dev, _ = db.eri_tensor(1.0e-8, to_host=False)
+    db.plan(1.0e-8, 0, 1)
+    for k in keys:
+        Dt, Da, Db = g["Dt" + k], g["Da" + k], g["Db" + k]
+        ref = (g["J" + k], g["Xa" + k], g["Xb" + k])
+        scale = max(1.0, max(np.abs(r).max() for r in ref))
+        for got in (db.jk_stored(G_dev, Dt, Da, Db), db.jk_direct(Dt, Da, Db),
+                    db.jk_direct(Dt, Da, Db, variant=eng.GEN)):
+            for mine, r in zip(got, ref):
+                assert np.abs(mine - r).max() < JK_TOL * scale
+    db.close()
+
+
+def test_jk_variants_rhf_uhf(eng, gold):
+    g = gold("h2o_631gss.npz")
+    db = _basis(eng, "h2o")
+    db.plan(1.0e-8, 0, 1)
+    G = g["G"]
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-1, 1, (24, 24)); Da = 0.5 * (X + X.T)
+    X = rng.uniform(-1, 1, (24, 24)); Db = 0.5 * (X + X.T)
+    # RHF-shaped (Da == Db) and UHF-shaped, against the reference's einsum patterns
+    for a, b, variant in ((Da, Da, eng.RHF), (Da, Db, eng.UHF)):
+        J = np.einsum("cd,abcd->ab", a + b, G)
+        Xa = np.einsum("cb,abcd->ad", -a, G)
+        Xb = np.einsum("cb,abcd->ad", -b, G)
+        assert eng.classify_densities(a + b, a, b) == variant
+        got = db.jk_direct(a + b, a, b)
+        for mine, r in zip(got, (J, Xa, Xb)):
+            assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
+    db.close()
+
+
+# --------------------------------------------------------------------------------------------
+# against the CPU oracle on seeded inputs
+# --------------------------------------------------------------------------------------------
+def test_water_trimer_full_tensor_vs_oracle(eng):
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    rng = np.random.default_rng(42)
+    coords = S.water_cluster(3)
+    for row in coords:                      # break the lattice symmetry
+        for k in (2, 3, 4):
+            row[k] += float(rng.uniform(-0.15, 0.15))
+    mol = S.Molecule(coords, "6-31G**")
+    db = eng.DeviceBasis(mol)
+    bounds, pmax = db.schwarz()
+    ob = oracle.OracleBasis(db.table)
+    ob_bounds, ob_pmax = ob.schwarz()
+    assert np.abs(bounds - ob_bounds).max() < 1e-12
+    G_dev, G = db.eri_tensor(1.0e-8, to_host=True)
+    G_ref, nsurv = ob.tensor(1.0e-8)
+    assert np.abs(G - G_ref).max() < ERI_TOL
+    # identical screening decisions: the zero patterns agree block by block
+    assert np.array_equal(G == 0.0, G_ref == 0.0) or np.abs(G[G_ref == 0.0]).max() < 1e-13
+    db.close()
+
+
+def test_edge_cases(eng):
+    """Single shell, single atom, far-apart atoms (asymptotic Boys branch), coincident centres
+    (T = 0 branch)."""
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    cases = [
+        [["H", 1.0, 0.0, 0.0, 0.0]],
+        [["O", 8.0, 0.0, 0.0, 0.0]],
+        [["O", 8.0, 0.0, 0.0, 0.0], ["O", 8.0, 0.0, 0.0, 9.0]],
+        [["H", 1.0, 0.0, 0.0, 0.0], ["H", 1.0, 0.0, 0.0, 1.0e-9]],
+    ]
+    for coords in cases:
+        mol = S.Molecule(coords, "6-31G**")
+        db = eng.DeviceBasis(mol)
+        db.schwarz()
+        _, G = db.eri_tensor(1.0e-8, to_host=True)
+        G_ref, _ = oracle.OracleBasis(db.table).tensor(1.0e-8)
+        assert np.abs(G - G_ref).max() < ERI_TOL
+        db.close()
+
+
+def test_errors_are_loud(eng):
+    from pychem_b200 import _lib, structures as S
+    mol = S.Molecule([["O", 8.0, 0.0, 0.0, 0.0]], "6-31G**", cartesian_l=[2])
+    with pytest.raises(_lib.PychemB200Error):
+        eng.DeviceBasis(mol)               # Cartesian d is refused, not silently mis-computed
+    db = _basis(eng, "h2")
+    with pytest.raises(_lib.PychemB200Error):
+        db.eri_quartets([(1, 0, 0, 0)])    # a > b
+    db.close()
+
+
+# --------------------------------------------------------------------------------------------
+# full-size, size-independent properties: (H2O)8 6-31G** (N = 192)
+# --------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def water8(eng):
+    from pychem_b200 import structures as S
+    db = eng.DeviceBasis(S.Molecule(S.water_cluster(8), "6-31G**"))
+    db.schwarz()
+    yield db
+    db.close()
+
+
+def _sym(rng, n):
+    X = rng.uniform(-1, 1, (n, n))
+    return 0.5 * (X + X.T)
+
+
+def test_full_size_direct_equals_stored(eng, water8):
+    db = water8
+    N = db.nbf
+    assert N == 192
+    G_dev, _ = db.eri_tensor(1.0e-8, to_host=False)
+    db.plan(1.0e-8, 0, 1)
+    rng = np.random.default_rng(7)
+    Da, Db = _sym(rng, N), _sym(rng, N)
+    stored = db.jk_stored(G_dev, Da + Db, Da, Db)
+    direct = db.jk_direct(Da + Db, Da, Db)
+    for s, d in zip(stored, direct):
+        assert np.abs(s - d).max() < 1e-9 * max(1.0, np.abs(s).max())
+    # non-symmetric (NOCI-shaped) densities through the general variant
+    A, B = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    stored = db.jk_stored(G_dev, A + B, A, B)
+    direct = db.jk_direct(A + B, A, B)
+    for s, d in zip(stored, direct):
+        assert np.abs(s - d).max() < 1e-9 * max(1.0, np.abs(s).max())
+    del G_dev
+
+
+def test_full_size_linearity_symmetry_partition(eng, water8):
+    db = water8
+    N = db.nbf
+    rng = np.random.default_rng(8)
+    D1, D2 = _sym(rng, N), _sym(rng, N)
+    db.plan(1.0e-8, 0, 1)
+    J1, X1, _ = db.jk_direct(2 * D1, D1, D1)
+    J2, X2, _ = db.jk_direct(2 * D2, D2, D2)
+    J12, X12, _ = db.jk_direct(2 * (D1 + D2), D1 + D2, D1 + D2)
+    scale = np.abs(J12).max()
+    assert np.abs(J1 + J2 - J12).max() < 1e-10 * scale
+    assert np.abs(X1 + X2 - X12).max() < 1e-10 * scale
+    assert np.abs(J12 - J12.T).max() < 1e-10 * scale
+    assert np.abs(X12 - X12.T).max() < 1e-10 * scale
+    # energy-like invariant: sum(D1*J(D2)) == sum(D2*J(D1))
+    assert abs(np.sum(D1 * J2) - np.sum(D2 * J1)) < 1e-9 * abs(np.sum(D1 * J2))
+    # static partition: the accumulators of 3 ranks add up to the 1-rank result
+    import torch
+    from pychem_b200 import _lib, dist
+    total = torch.zeros(3 * N * N, dtype=torch.float64, device="cuda")
+    quartets = 0
+    for r in range(3):
+        c = db.plan(1.0e-8, r, 3)
+        quartets += c["my_quartets"]
+        acc = db.accumulator()
+        Dt1 = np.ascontiguousarray(2 * D1)
+        _lib.check(db.lib.pc_jk_direct_accumulate(db.h, eng.RHF, eng._ptr(Dt1), eng._ptr(D1), eng._ptr(D1), eng._ptr(acc)))
+        torch.cuda.synchronize()
+        total += acc
+    assert quartets == c["all_quartets"]
+    J, Xa, _ = dist.finalize_accumulators(total.cpu().numpy(), N, eng.RHF)
+    assert np.abs(J - J1).max() < 1e-10 * scale
+    assert np.abs(Xa - X1).max() < 1e-10 * scale
+    db.plan(1.0e-8, 0, 1)
