@@ -103,6 +103,9 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
  *   pc_jk_finalize: turns the summed accumulators into J, Xa, Xb (symmetrisation and sign).
  *   pc_jk_direct: both steps on one GPU with an internal accumulator.
  */
+/* variant 5 (measurement only): generate every ERI of the slice and discard it -- the pure
+ * ERI-generation time of the same schedule, no digestion. */
+#define PC_ERI_ONLY 5
 int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const double* Da,
                             const double* Db, double* acc_dev);
 int pc_jk_finalize(pc_basis* h, int variant, const double* acc_dev, double* J, double* Xa,

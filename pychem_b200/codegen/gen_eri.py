@@ -253,51 +253,28 @@ class ClassGen:
         return em.lines + out
 
     # ------------------------------------------------------------------ file
-    def source(self):
-        lx1, ly1, lx2, ly2 = self.l
-        vrr = self.gen_vrr()
-        tail = self.gen_tail()
-        NA, NB, NC, ND = self.nsph
-        nsp = NA * NB * NC * ND
-        nmax = max(self.La, self.Lc, 1)
-        block = 128 if self.L <= 4 else 64
-        s = []
-        s.append("// GENERATED by pychem_b200/codegen/gen_eri.py -- do not edit.")
-        s.append("// class (%s%s|%s%s): L=%d, %d x %d contracted (e0|f0), %d VRR temporaries, %d tail temporaries"
-                 % (LNAME[lx1], LNAME[ly1], LNAME[lx2], LNAME[ly2], self.L, self.ne, self.nf, self.n_vrr, self.n_tail))
-        s.append('#include "../pc_common.cuh"')
-        s.append("")
-        s.append("namespace {")
-        s.append("constexpr int L = %d, NE = %d, NF = %d, NSPH = %d;" % (self.L, self.ne, self.nf, nsp))
-        s.append("")
-        s.append("template <int MODE>")
-        s.append("__global__ void __launch_bounds__(%d) eri_%s_kernel(const PcEriArgs A) {" % (block, self.name))
-        s.append("  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-        s.append("  int i, j;")
-        s.append("  if (!pc_decode_task(A, t, i, j)) return;")
-        s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = A.bra.K, KK = A.ket.K;")
-        s.append("  const double AB0 = A.bra.xy[i], AB1 = A.bra.xy[nb + i], AB2 = A.bra.xy[2 * nb + i];")
-        s.append("  const double CD0 = A.ket.xy[j], CD1 = A.ket.xy[nk + j], CD2 = A.ket.xy[2 * nk + j];")
-        s.append("  double acc[NE * NF];")
-        s.append("#pragma unroll")
-        s.append("  for (int k = 0; k < NE * NF; ++k) acc[k] = 0.0;")
+    V2 = False
+
+    def prim_prologue(self, s, nmax):
+        """Primitive loops: ket primitives outside (per-lane, coalesced loads, once per ket
+        primitive), bra primitives inside (warp-uniform addresses -> broadcast loads)."""
         s.append("  const double* __restrict__ bp = A.bra.prim + i;")
         s.append("  const double* __restrict__ kp = A.ket.prim + j;")
         s.append("  const size_t sb = (size_t)KB * nb, sk = (size_t)KK * nk;")
-        s.append("  for (int ib = 0; ib < KB; ++ib) {")
-        s.append("    const double sP = bp[(size_t)ib * nb], UP = bp[sb + (size_t)ib * nb];")
-        s.append("    const double Px = bp[2 * sb + (size_t)ib * nb], Py = bp[3 * sb + (size_t)ib * nb], Pz = bp[4 * sb + (size_t)ib * nb];")
-        s.append("    const double kzP = bp[5 * sb + (size_t)ib * nb];")
-        s.append("    const double zeta = 0.5 * sP;")
-        s.append("    const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;")
+        s.append("  for (int ik = 0; ik < KK; ++ik) {")
+        s.append("    const double sQ = __ldg(kp + (size_t)ik * nk), UQ = __ldg(kp + sk + (size_t)ik * nk);")
+        s.append("    const double Qx = __ldg(kp + 2 * sk + (size_t)ik * nk), Qy = __ldg(kp + 3 * sk + (size_t)ik * nk), Qz = __ldg(kp + 4 * sk + (size_t)ik * nk);")
+        s.append("    const double kzQ = __ldg(kp + 5 * sk + (size_t)ik * nk);")
+        s.append("    const double eta = 0.5 * sQ;")
+        s.append("    const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;")
         for n in range(1, nmax + 1):
-            s.append("    const double nz%d = %d.0 * zeta;" % (n, n))
-        s.append("    for (int ik = 0; ik < KK; ++ik) {")
-        s.append("      const double sQ = kp[(size_t)ik * nk], UQ = kp[sk + (size_t)ik * nk];")
-        s.append("      const double Qx = kp[2 * sk + (size_t)ik * nk], Qy = kp[3 * sk + (size_t)ik * nk], Qz = kp[4 * sk + (size_t)ik * nk];")
-        s.append("      const double kzQ = kp[5 * sk + (size_t)ik * nk];")
-        s.append("      const double eta = 0.5 * sQ;")
-        s.append("      const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;")
+            s.append("    const double ne%d = %d.0 * eta;" % (n, n))
+        s.append("    for (int ib = 0; ib < KB; ++ib) {")
+        s.append("      const double sP = __ldg(bp + (size_t)ib * nb), UP = __ldg(bp + sb + (size_t)ib * nb);")
+        s.append("      const double Px = __ldg(bp + 2 * sb + (size_t)ib * nb), Py = __ldg(bp + 3 * sb + (size_t)ib * nb), Pz = __ldg(bp + 4 * sb + (size_t)ib * nb);")
+        s.append("      const double kzP = __ldg(bp + 5 * sb + (size_t)ib * nb);")
+        s.append("      const double zeta = 0.5 * sP;")
+        s.append("      const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;")
         s.append("      const double R0 = Px - Qx, R1 = Py - Qy, R2_ = Pz - Qz;")
         s.append("      const double Rsq = R0 * R0 + R1 * R1 + R2_ * R2_;")
         s.append("      double F[L + 1];")
@@ -306,9 +283,48 @@ class ClassGen:
         s.append("      const double Re0 = R0 * eta, Re1 = R1 * eta, Re2 = R2_ * eta;")
         s.append("      const double ze = zeta * eta;")
         for n in range(1, nmax + 1):
-            s.append("      const double ne%d = %d.0 * eta; const double nze%d = %d.0 * ze;" % (n, n, n, n))
+            s.append("      const double nz%d = %d.0 * zeta; const double nze%d = %d.0 * ze;" % (n, n, n, n))
         s.append("      (void)QX0; (void)QX1; (void)QX2; (void)PX0; (void)PX1; (void)PX2; (void)ze;")
         s.append("      (void)Rz0; (void)Rz1; (void)Rz2; (void)Re0; (void)Re1; (void)Re2;")
+
+    def block_size(self):
+        return 128 if self.L <= 4 else 64
+
+    def min_blocks(self):
+        return 8 if self.L == 0 else 1
+
+    def source(self):
+        lx1, ly1, lx2, ly2 = self.l
+        vrr = self.gen_vrr()
+        tail = self.gen_tail()
+        NA, NB, NC, ND = self.nsph
+        nsp = NA * NB * NC * ND
+        nmax = max(self.La, self.Lc, 1)
+        block = self.block_size()
+        s = []
+        s.append("// GENERATED by pychem_b200/codegen/gen_eri.py -- do not edit.")
+        s.append("// class (%s%s|%s%s)%s: L=%d, %d x %d contracted (e0|f0), %d VRR temporaries, %d tail temporaries"
+                 % (LNAME[lx1], LNAME[ly1], LNAME[lx2], LNAME[ly2], " [rolled form]" if self.V2 else "",
+                    self.L, self.ne, self.nf, self.n_vrr, self.n_tail))
+        s.append('#include "../pc_common.cuh"')
+        s.append("")
+        s.append("namespace {")
+        s.append("constexpr int L = %d, NE = %d, NF = %d, NSPH = %d;" % (self.L, self.ne, self.nf, nsp))
+        s.extend(self.tables())
+        s.append("")
+        s.append("template <int MODE>")
+        s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const PcEriArgs A) {" % (block, self.min_blocks(), self.name))
+        s.append("  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+        s.append("  int i, j;")
+        s.append("  if (!pc_decode_task(A, t, i, j)) return;")
+        s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = A.bra.K, KK = A.ket.K;")
+        s.append("  const double AB0 = __ldg(A.bra.xy + i), AB1 = __ldg(A.bra.xy + nb + i), AB2 = __ldg(A.bra.xy + 2 * nb + i);")
+        s.append("  const double CD0 = __ldg(A.ket.xy + j), CD1 = __ldg(A.ket.xy + nk + j), CD2 = __ldg(A.ket.xy + 2 * nk + j);")
+        s.append("  double acc[NE * NF];")
+        s.append("#pragma unroll%s" % (" 1" if self.V2 else ""))
+        s.append("  for (int k = 0; k < NE * NF; ++k) acc[k] = 0.0;")
+        s.extend(self.scratch_decls())
+        self.prim_prologue(s, nmax)
         for line in vrr:
             s.append("      " + line)
         s.append("    }")
@@ -326,13 +342,282 @@ class ClassGen:
         s.append("  const int block = %d;" % block)
         s.append("  const unsigned grid = (unsigned)((A.t_count + block - 1) / block);")
         s.append("  switch (mode) {")
-        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN"):
+        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL"):
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")
         s.append("  return cudaGetLastError();")
         s.append("}")
         return "\n".join(s) + "\n"
+
+    def tables(self):
+        return []
+
+    def scratch_decls(self):
+        return []
+
+
+class ClassGenV2(ClassGen):
+    """Rolled form for the large classes.  Same recursion, same arithmetic per element, but
+      * the bra build is a rolled loop over the ket Cartesian component (one code body per ket
+        shell): the recursion over the bra components runs in registers for one ket component
+        at a time; the one term that couples ket components, [a-1|c-1_i]^(m+1)
+        (two_electron_vrr.c:104-108), is read from a small per-thread scratch array written
+        while the previous ket shell was processed;
+      * the ket HRR + cart->spherical is one code body in a rolled loop over the bra (e0| components,
+        the bra HRR + cart->spherical one body in a rolled loop over the ket spherical components.
+    The fully straight-line form of these classes (up to 8000 FMAs in one basic block with
+    thousands of live values) makes ptxas fall back to spilling everything."""
+    V2 = True
+
+    def __init__(self, *cls):
+        ClassGen.__init__(self, *cls)
+        self.layout()
+
+    def shell_needs(self):
+        lx1, ly1, lx2, ly2 = self.l
+        need = {}
+        stack = [(la, lc, 0) for la in range(lx1, self.La + 1) for lc in range(lx2, self.Lc + 1)]
+        while stack:
+            la, lc, m = stack.pop()
+            if la < 0 or lc < 0:
+                continue
+            if m in need.setdefault((la, lc), set()):
+                continue
+            need[(la, lc)].add(m)
+            if la > 0:
+                stack += [(la - 1, lc, m), (la - 1, lc, m + 1)]
+                if la >= 2:
+                    stack += [(la - 2, lc, m), (la - 2, lc, m + 1)]
+                if lc >= 1:
+                    stack.append((la - 1, lc - 1, m + 1))
+            elif lc > 0:
+                stack += [(0, lc - 1, m), (0, lc - 1, m + 1)]
+                if lc >= 2:
+                    stack += [(0, lc - 2, m), (0, lc - 2, m + 1)]
+        return need
+
+    def layout(self):
+        self.need = self.shell_needs()
+        La, Lc = self.La, self.Lc
+        # values of ket shell lc that the NEXT ket shell reads through the cross term
+        self.store = {}
+        for lc in range(Lc):
+            for la in range(La):
+                src = self.need.get((la + 1, lc + 1), set())
+                self.store[(la, lc)] = sorted(m + 1 for m in src)
+        self.MS = {}
+        for lc in range(Lc):
+            mx = [max(self.store[(la, lc)]) for la in range(La) if self.store[(la, lc)]]
+            self.MS[lc] = max(mx) if mx else 0
+        self.nslot = ncum(La - 1)
+        self.xs_size = max([self.nslot * ncart(lc) * self.MS[lc] for lc in range(Lc)] + [1])
+
+    def tables(self):
+        out = []
+        for lc in range(1, self.Lc + 1):
+            cm, cv = [], []
+            for c in comps(lc):
+                for d in range(3):
+                    if c[d] > 0:
+                        cm.append(cidx(dec(c, d)))
+                        cv.append(float(c[d]))
+                    else:
+                        cm.append(0)
+                        cv.append(0.0)
+            out.append("__device__ const int CM%d[%d] = {%s};" % (lc, len(cm), ", ".join(str(x) for x in cm)))
+            out.append("__device__ const double CV%d[%d] = {%s};" % (lc, len(cv), ", ".join(repr(x) for x in cv)))
+        return out
+
+    def scratch_decls(self):
+        return ["  double KV[%d];" % (ncum(self.Lc) * (self.L + 1)),
+                "  double XSA[%d], XSB[%d];" % (self.xs_size, self.xs_size)]
+
+    def gen_vrr(self):
+        lx1, ly1, lx2, ly2 = self.l
+        La, Lc, L = self.La, self.Lc, self.L
+        M1 = L + 1
+        zero = (0, 0, 0)
+        need = self.need
+        lines = []
+        self.vrr_refs = 0
+        ntemp = 0
+        # ---- ket build on the s bra, straight-line, results to KV[c*M1+m]
+        em = Emit("k")
+        kv = {}
+        for m in sorted(need.get((0, 0), [])):
+            kv[(zero, m)] = "F[%d]" % m
+            em.raw("KV[%d] = F[%d];" % (m, m))
+        for lc in range(1, Lc + 1):
+            for c in comps(lc):
+                d = first_dir(c)
+                c0 = dec(c, d)
+                n = c0[d]
+                for m in sorted(need.get((0, lc), [])):
+                    expr = "fma(QX%d, %s, Re%d * %s)" % (d, kv[(c0, m)], d, kv[(c0, m + 1)])
+                    self.vrr_refs += 2 + (2 if n > 0 else 0)
+                    if n > 0:
+                        c1 = dec(c0, d)
+                        expr = "fma(ne%d, fma(-eta, %s, %s), %s)" % (n, kv[(c1, m + 1)], kv[(c1, m)], expr)
+                    v = em.new(expr)
+                    kv[(c, m)] = v
+                    em.raw("KV[%d] = %s;" % (cum(c) * M1 + m, v))
+        ntemp += em.n
+        lines += em.lines
+        # ---- bra build, one rolled loop per ket shell
+        e_index = {c: i for i, c in enumerate(self.e_list)}
+        foff = {}
+        o = 0
+        for lf in range(lx2, Lc + 1):
+            foff[lf] = o
+            o += ncart(lf)
+        for lc in range(0, Lc + 1):
+            if not any(need.get((la, lc)) for la in range(1, La + 1)):
+                continue
+            cur = "XSA" if lc % 2 == 0 else "XSB"
+            prev = "XSB" if lc % 2 == 0 else "XSA"
+            NCc = ncart(lc)
+            em = Emit("w%d_" % lc)
+            lines.append("#pragma unroll 1")
+            lines.append("for (int ic = 0; ic < %d; ++ic) {" % NCc)
+            body = []
+            V = {}
+            for m in sorted(need.get((0, lc), [])):
+                V[(zero, m)] = "b%d_%d" % (lc, m)
+                body.append("const double b%d_%d = KV[(%d + ic) * %d + %d];" % (lc, m, ncum(lc - 1), M1, m))
+            if lc >= 1:
+                for d in range(3):
+                    body.append("const int cs%d = CM%d[ic * 3 + %d] * %d;" % (d, lc, d, self.MS[lc - 1]))
+                    body.append("const double cz%d = CV%d[ic * 3 + %d] * ze;" % (d, lc, d))
+            for la in range(1, La + 1):
+                ms = sorted(need.get((la, lc), []))
+                if not ms:
+                    continue
+                for a in comps(la):
+                    d = first_dir(a)
+                    a0 = dec(a, d)
+                    n = a0[d]
+                    for m in ms:
+                        expr = "fma(PX%d, %s, Rz%d * %s)" % (d, V[(a0, m)], d, V[(a0, m + 1)])
+                        # executed once per ket component; the cross term exists for the
+                        # components with c_d > 0 only (counted as in the straight-line form)
+                        self.vrr_refs += NCc * (2 + (2 if n > 0 else 0)) + sum(1 for c in comps(lc) if c[d] > 0)
+                        if n > 0:
+                            a1 = dec(a0, d)
+                            expr = "fma(nz%d, fma(-zeta, %s, %s), %s)" % (n, V[(a1, m + 1)], V[(a1, m)], expr)
+                        if lc >= 1:
+                            base = cum(a0) * ncart(lc - 1) * self.MS[lc - 1] + m      # (m+1) - 1
+                            expr = "fma(cz%d, %s[%d + cs%d], %s)" % (d, prev, base, d, expr)
+                        V[(a, m)] = em.new(expr)
+            body += em.lines
+            # stores for the next ket shell
+            if lc < Lc:
+                for la in range(0, La):
+                    for a in comps(la):
+                        for mp in self.store[(la, lc)]:
+                            body.append("%s[%d + ic * %d] = %s;" % (cur, cum(a) * NCc * self.MS[lc] + (mp - 1),
+                                                                    self.MS[lc], V[(a, mp)]))
+            # contraction
+            if lc >= lx2:
+                for ie, e in enumerate(self.e_list):
+                    body.append("acc[%d + ic] += %s;" % (ie * self.nf + foff[lc], V[(e, 0)]))
+            lines += ["  " + b for b in body]
+            lines.append("}")
+            ntemp += em.n * NCc
+        self.n_vrr = ntemp
+        return lines
+
+    def gen_tail(self):
+        lx1, ly1, lx2, ly2 = self.l
+        self.hrr_el = 0
+        self.c2s_ops = 0
+        f_index = {c: i for i, c in enumerate(self.f_list)}
+        e_index = {c: i for i, c in enumerate(self.e_list)}
+        nqs = nsph(lx2) * nsph(ly2)
+        nps = nsph(lx1) * nsph(ly1)
+        lines = ["double ks[%d];" % (self.ne * nqs)]
+        # ---- ket HRR + cart->sph, rolled over the bra (e0| component
+        em = Emit("hk")
+        memo = {}
+
+        def hk(cx, cy):
+            key = (cx, cy)
+            if key in memo:
+                return memo[key]
+            if sum(cy) == 0:
+                val = "ar[%d]" % f_index[cx]
+            else:
+                d = first_dir(cy)
+                cy0 = dec(cy, d)
+                val = em.new("fma(CD%d, %s, %s)" % (d, hk(cx, cy0), hk(inc(cx, d), cy0)))
+                self.hrr_el += self.ne
+            memo[key] = val
+            return val
+
+        cart = {(ix, iy): hk(cx, cy) for ix, cx in enumerate(comps(lx2)) for iy, cy in enumerate(comps(ly2))}
+        half = {}
+        for ix in range(ncart(lx2)):
+            for my, row in enumerate(c2s_rows(ly2)):
+                half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
+        outs = []
+        for mx, row in enumerate(c2s_rows(lx2)):
+            for my in range(nsph(ly2)):
+                v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
+                outs.append("ks[ie * %d + %d] = %s;" % (nqs, mx * nsph(ly2) + my, v))
+        lines.append("#pragma unroll 1")
+        lines.append("for (int ie = 0; ie < %d; ++ie) {" % self.ne)
+        lines.append("  const double* __restrict__ ar = acc + ie * %d;" % self.nf)
+        lines += ["  " + x for x in em.lines + outs]
+        lines.append("}")
+        ops1 = em.ops * self.ne
+        n1 = em.n
+        # ---- bra HRR + cart->sph, rolled over the ket spherical component
+        em = Emit("hb")
+        memo = {}
+
+        def hb(cx, cy):
+            key = (cx, cy)
+            if key in memo:
+                return memo[key]
+            if sum(cy) == 0:
+                val = "kr[%d]" % (e_index[cx] * nqs)
+            else:
+                d = first_dir(cy)
+                cy0 = dec(cy, d)
+                val = em.new("fma(AB%d, %s, %s)" % (d, hb(cx, cy0), hb(inc(cx, d), cy0)))
+                self.hrr_el += nqs
+            memo[key] = val
+            return val
+
+        cart = {(ix, iy): hb(cx, cy) for ix, cx in enumerate(comps(lx1)) for iy, cy in enumerate(comps(ly1))}
+        half = {}
+        for ix in range(ncart(lx1)):
+            for my, row in enumerate(c2s_rows(ly1)):
+                half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
+        outs = []
+        for mx, row in enumerate(c2s_rows(lx1)):
+            for my in range(nsph(ly1)):
+                v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
+                outs.append("g[%d + q] = %s;" % ((mx * nsph(ly1) + my) * nqs, v))
+        lines.append("#pragma unroll 1")
+        lines.append("for (int q = 0; q < %d; ++q) {" % nqs)
+        lines.append("  const double* __restrict__ kr = ks + q;")
+        lines += ["  " + x for x in em.lines + outs]
+        lines.append("}")
+        self.c2s_ops = ops1 + em.ops * nqs
+        self.n_tail = n1 + em.n
+        return lines
+
+
+V2_THRESHOLD = 600      # classes with more VRR temporaries than this use the rolled form
+
+
+def make_class(cls):
+    g = ClassGen(*cls)
+    g.gen_vrr()
+    if g.n_vrr > V2_THRESHOLD:
+        return ClassGenV2(*cls)
+    return ClassGen(*cls)
 
 
 def flop_model(g):
@@ -365,7 +650,7 @@ def main(outdir):
     names = []
     model = {}
     for cls in all_classes():
-        g = ClassGen(*cls)
+        g = make_class(cls)
         path = os.path.join(outdir, "eri_%s.cu" % g.name)
         src = g.source()
         model[g.name] = flop_model(g)
@@ -384,6 +669,13 @@ def main(outdir):
         row = []
         for ik, k in enumerate(PAIR_CLASSES):
             row.append("pc_launch_%s" % "".join(LNAME[x] for x in b + k) if ik <= ib else "nullptr")
+        tab.append("  {" + ", ".join(row) + "},")
+    tab.append("};")
+    tab.append("int pc_block_table[6][6] = {")
+    for ib, b in enumerate(PAIR_CLASSES):
+        row = []
+        for ik, k in enumerate(PAIR_CLASSES):
+            row.append(str(make_class(b + k).block_size()) if ik <= ib else "0")
         tab.append("  {" + ", ".join(row) + "},")
     tab.append("};")
     import json

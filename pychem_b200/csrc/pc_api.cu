@@ -15,7 +15,6 @@
 #include <string>
 #include <vector>
 
-extern pc_launch_fn pc_launch_table[6][6];
 
 namespace {
 
@@ -94,6 +93,7 @@ struct PlanItem {
   long long total;      // all tasks of the bucket pair
   long long begin, count;  // this rank's slice
   DevBuf<long long>* off;
+  DevBuf<int>* blk_i0;
 };
 
 bool is_device_ptr(const void* p) {
@@ -256,18 +256,28 @@ struct pc_basis {
   int rank = 0, nranks = 1;
   std::vector<PlanItem> plan;
   std::vector<DevBuf<long long>*> plan_bufs;
+  std::vector<DevBuf<int>*> plan_ibufs;
   long long my_quartets = 0, my_eris = 0, all_quartets = 0, all_eris = 0;
   // scratch
   DevBuf<double> acc, dstage, ostage;
   long long launches = 0;
+  // side streams: the (bra bucket, ket bucket) launches of one Fock build are independent
+  // (they only meet in the atomics), so they are spread round-robin to overlap their tails
+  std::vector<cudaStream_t> side;
+  cudaEvent_t ev_fork = nullptr;
+  std::vector<cudaEvent_t> ev_join;
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;     // one before every plan item + one after the last
   std::vector<float> prof_ms;               // per plan item, from the last accumulate
 
   ~pc_basis() {
     for (auto e : prof_events) cudaEventDestroy(e);
+    for (auto e : ev_join) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    for (auto st : side) cudaStreamDestroy(st);
     for (auto* k : kinds) delete k;
     for (auto* b : plan_bufs) delete b;
+    for (auto* b : plan_ibufs) delete b;
     if (stream) cudaStreamDestroy(stream);
   }
   size_t pair_index(int a, int b) const { return (size_t)a * nshell - (size_t)a * (a - 1) / 2 + (b - a); }
@@ -327,14 +337,15 @@ int upload_kind(pc_basis* h, Kind* k) {
   return 0;
 }
 
-int launch_class(pc_basis* h, int mode, const Kind* kb, const Kind* kk, PcEriArgs& A) {
+int launch_class(pc_basis* h, int mode, const Kind* kb, const Kind* kk, PcEriArgs& A,
+                 cudaStream_t st = nullptr) {
   pc_launch_fn fn = pc_launch_table[kb->pc][kk->pc];
   if (!fn) return fail("internal: no kernel for this class order");
   A.bra = kb->view();
   A.ket = kk->view();
   A.boys = h->boys.p;
   A.nbf = h->nbf;
-  cudaError_t e = fn(mode, A, h->stream);
+  cudaError_t e = fn(mode, A, st ? st : h->stream);
   if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
   h->launches += 1;
   return 0;
@@ -517,6 +528,8 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
   if (!(h->planned && h->thresh == thresh && h->rank == rank && h->nranks == nranks)) {
     for (auto* b : h->plan_bufs) delete b;
     h->plan_bufs.clear();
+    for (auto* b : h->plan_ibufs) delete b;
+    h->plan_ibufs.clear();
     h->plan.clear();
     h->my_quartets = h->my_eris = h->all_quartets = h->all_eris = 0;
     const int nk = (int)h->kinds.size();
@@ -549,12 +562,36 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         it.off = new DevBuf<long long>();
         h->plan_bufs.push_back(it.off);
         PC_CUDA(it.off->upload(off, h->stream));
+        {
+          // bra pair of every block's first task (block size is a property of the class kernel)
+          const int bs = pc_block_table[B->pc][Kt->pc];
+          const long long nblk = (it.count + bs - 1) / bs;
+          std::vector<int> i0((size_t)nblk);
+          int cur = 0;
+          for (long long b = 0; b < nblk; ++b) {
+            const long long g0 = it.begin + b * bs;
+            while (off[cur + 1] <= g0) ++cur;
+            i0[(size_t)b] = cur;
+          }
+          it.blk_i0 = new DevBuf<int>();
+          h->plan_ibufs.push_back(it.blk_i0);
+          PC_CUDA(it.blk_i0->upload(i0, h->stream));
+        }
         PC_CUDA(cudaStreamSynchronize(h->stream));
         const long long nsph = (long long)(2 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
         h->all_quartets += total; h->all_eris += total * nsph;
         h->my_quartets += it.count; h->my_eris += it.count * nsph;
         h->plan.push_back(it);
       }
+    // longest-first launch order (rough cost ~ quartets * primitive quartets * (L+1)^3)
+    auto cost = [&](const PlanItem& it) {
+      const Kind* B = h->kinds[it.kb];
+      const Kind* Kt = h->kinds[it.kk];
+      const double L1 = B->lx + B->ly + Kt->lx + Kt->ly + 1;
+      return (double)it.count * ((double)B->K * Kt->K + 4.0) * L1 * L1 * L1;
+    };
+    std::stable_sort(h->plan.begin(), h->plan.end(),
+                     [&](const PlanItem& a, const PlanItem& b) { return cost(a) > cost(b); });
     h->planned = true;
     h->thresh = thresh; h->rank = rank; h->nranks = nranks;
   }
@@ -640,7 +677,7 @@ int pc_eri_tensor(pc_basis* h, double* G_dev, double* G_host) {
   for (const PlanItem& it : h->plan) {
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.off = it.off->p; A.same_kind = it.same; A.t_begin = it.begin; A.t_count = it.count;
+    A.off = it.off->p; A.blk_i0 = it.blk_i0->p; A.same_kind = it.same; A.t_begin = it.begin; A.t_count = it.count;
     A.G = G_dev;
     if (launch_class(h, PC_MODE_TENSOR, h->kinds[it.kb], h->kinds[it.kk], A)) return 1;
   }
@@ -689,7 +726,7 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
 int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const double* Da,
                             const double* Db, double* acc_dev) {
   if (!h || !Dt || !Da || !acc_dev) return fail("pc_jk_direct_accumulate: null");
-  if (variant != PC_JK_RHF && variant != PC_JK_UHF && variant != PC_JK_GEN)
+  if (variant != PC_JK_RHF && variant != PC_JK_UHF && variant != PC_JK_GEN && variant != PC_MODE_NULL)
     return fail("pc_jk_direct_accumulate: bad variant");
   if (!h->planned) return fail("pc_jk_direct_accumulate: call pc_plan first");
   if (!is_device_ptr(acc_dev)) return fail("pc_jk_direct_accumulate: acc_dev must be device memory");
@@ -708,6 +745,21 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
       h->prof_events.push_back(e);
     }
   }
+  const int NSIDE = 8;
+  const bool fan = !h->profiling && h->plan.size() > 1;
+  if (fan) {
+    while ((int)h->side.size() < NSIDE) {
+      cudaStream_t st;
+      PC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      h->side.push_back(st);
+      cudaEvent_t e;
+      PC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_join.push_back(e);
+    }
+    if (!h->ev_fork) PC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PC_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    for (int s2 = 0; s2 < NSIDE; ++s2) PC_CUDA(cudaStreamWaitEvent(h->side[s2], h->ev_fork, 0));
+  }
   size_t idx = 0;
   for (const PlanItem& it : h->plan) {
     if (h->profiling) PC_CUDA(cudaEventRecord(h->prof_events[idx], h->stream));
@@ -715,10 +767,18 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
     if (it.count == 0) continue;
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.off = it.off->p; A.same_kind = it.same; A.t_begin = it.begin; A.t_count = it.count;
+    A.off = it.off->p; A.blk_i0 = it.blk_i0->p; A.same_kind = it.same; A.t_begin = it.begin; A.t_count = it.count;
     A.Dj = dt; A.Da = da; A.Db = db;
     A.Jacc = acc_dev; A.Kaacc = acc_dev + nn; A.Kbacc = acc_dev + 2 * nn;
-    if (launch_class(h, variant, h->kinds[it.kb], h->kinds[it.kk], A)) return 1;
+    A.out = acc_dev;
+    if (launch_class(h, variant, h->kinds[it.kb], h->kinds[it.kk], A,
+                     fan ? h->side[idx % NSIDE] : h->stream)) return 1;
+  }
+  if (fan) {
+    for (int s2 = 0; s2 < NSIDE; ++s2) {
+      PC_CUDA(cudaEventRecord(h->ev_join[s2], h->side[s2]));
+      PC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[s2], 0));
+    }
   }
   if (h->profiling) {
     PC_CUDA(cudaEventRecord(h->prof_events[idx], h->stream));
