@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpychem_b200.so")
+LIB_PATH = os.environ.get("PYCHEM_B200_LIB", os.path.join(HERE, "libpychem_b200.so"))
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ip = ctypes.POINTER(ctypes.c_int)

@@ -291,7 +291,12 @@ class ClassGen:
         return 128 if self.L <= 4 else 64
 
     def min_blocks(self):
-        return 8 if self.L == 0 else 1
+        # occupancy floor: the low classes are latency-bound (ncu: long-scoreboard stalls), more
+        # resident warps beat a few spilled registers
+        override = os.environ.get("PC_GEN_MINB_L%d" % self.L)
+        if override:
+            return int(override)
+        return {0: 8, 1: 8}.get(self.L, 1)
 
     def source(self):
         lx1, ly1, lx2, ly2 = self.l

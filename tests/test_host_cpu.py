@@ -1,0 +1,122 @@
+"""CPU tests of the host logic and of the C-ABI library's loadability (no GPU, no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from pychem_b200 import _lib, dist, engine, structures as S
+from pychem_b200.basis_table import BasisTable
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    """include/pychem_b200.h is the contract: every function it declares must be exported by the
+    built shared library and bound in pychem_b200/_lib.py."""
+    header = open(os.path.join(ROOT, "include", "pychem_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 15
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built yet (python -m pychem_b200.build)")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "missing export: " + name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    _lib.load()
+
+
+def test_no_gpu_is_a_loud_error():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built yet")
+    with pytest.raises(_lib.PychemB200Error):
+        engine.DeviceBasis(helpers.molecule("h2"), device=0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pychem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").lower() or f in ("build.py",), f
+
+
+def test_basis_table_matches_reference_layout():
+    """Function order: atoms -> shells -> contiguous functions (Util/structures.py:511-520);
+    H2O 6-31G**: O s,s,p,s,p,d ; H s,s,p ; N = 24."""
+    t = BasisTable(helpers.molecule("h2o"))
+    assert t.nshell == 12 and t.nbf == 24
+    assert list(t.l) == [0, 0, 1, 0, 1, 2, 0, 0, 1, 0, 0, 1]
+    assert list(t.K) == [6, 3, 3, 1, 1, 1, 3, 1, 1, 3, 1, 1]
+    assert list(t.first_fn) == [0, 1, 2, 5, 6, 9, 14, 15, 16, 19, 20, 21]
+    assert not t.is_cart.any()
+    # coordinates scaled with the reference's (non-CODATA) constant, Data/constants.py:2
+    assert abs(t.centres[0, 2] - 0.117790 * 1.8897161646320724) < 1e-15
+    # scaled contraction coefficients cc*(2a)^((l+1.5)/2), Util/structures.py:843
+    assert abs(t.scc[0] - 0.0018311 * (2 * 5484.6717) ** 0.75) < 1e-12
+
+
+@pytest.mark.parametrize("name,nshell,nbf", [("h2", 6, 6), ("lih", 7, 11), ("benzene", 48, 96)])
+def test_sizes_of_baseline_configs(name, nshell, nbf):
+    t = BasisTable(helpers.molecule(name))
+    assert (t.nshell, t.nbf) == (nshell, nbf)
+
+
+def test_water_cluster_and_names():
+    assert S.remove_punctuation("6-31G**") == "631GSS"
+    assert S.remove_punctuation("6-311G") == "6311G"
+    c = S.water_cluster(32)
+    assert len(c) == 96
+    m = S.Molecule(c, "6-31G**")
+    assert m.NOrbitals == 768 and m.NCgtf == 384
+    assert len(m.ShellPairs) == 73920
+    sp = m.ShellPairs[(3, 7)]
+    assert sp.Centre1.Ivec == [5] and sp.Ltot == 0
+
+
+def test_density_classification():
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, (5, 5))
+    Ds = 0.5 * (X + X.T)
+    assert engine.classify_densities(2 * Ds, Ds, Ds) == engine.RHF
+    assert engine.classify_densities(Ds + Ds.T, Ds, Ds.T.copy() + 0.0) == engine.RHF
+    Y = rng.uniform(-1, 1, (5, 5))
+    Dt = 0.5 * (Y + Y.T)
+    assert engine.classify_densities(Ds + Dt, Ds, Dt) == engine.UHF
+    assert engine.classify_densities(X + Y, X, Y) == engine.GEN
+
+
+def test_slice_bounds_partition_everything():
+    for total in (0, 1, 7, 1000003):
+        for n in (1, 2, 3, 8):
+            cuts = [dist.slice_bounds(total, r, n) for r in range(n)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == total
+            assert all(cuts[r][1] == cuts[r + 1][0] for r in range(n - 1))
+            sizes = [e - b for b, e in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_flop_model_matches_survey_table():
+    """pychem_b200/data/flop_model.json against SURVEY.md 8(d) (flop / primitive quartet).  The
+    p-only classes agree exactly; with d shells the generator contracts fewer (e0|f0) classes and
+    exploits the sparsity of the cart->spherical matrices, so its count is a few % LOWER (the
+    roofline fraction reported from it is therefore conservative)."""
+    import json
+    m = json.load(open(os.path.join(ROOT, "pychem_b200", "data", "flop_model.json")))
+    assert len(m) == 21
+    survey = {"ssss": 23, "psss": 48, "psps": 123, "ppss": 117, "ppps": 354, "pppp": 1023,
+              "dsss": 117, "dsps": 354, "dpss": 258, "dpps": 857, "dsds": 795, "dppp": 2468,
+              "ddss": 509, "dpds": 1932, "ddps": 1784, "dpdp": 4717, "ddpp": 5087, "ddds": 4067,
+              "dddp": 9744, "dddd": 18445}
+    for k, v in survey.items():
+        assert 0.94 * v <= m[k]["flop_prim"] <= v, (k, m[k]["flop_prim"], v)
+    for k in ("ssss", "psss", "psps", "ppss", "ppps", "pppp"):
+        assert m[k]["flop_prim"] == survey[k]
+    assert m["dddd"]["vrr_refs"] == 8122 and m["dddd"]["vrr_elems"] == 2321
