@@ -161,36 +161,43 @@ def reference_sample(n_waters, seconds, seed=1234):
 
     def bound(a, b):
         if (a, b) not in bound_cache:
-            blk = np.asarray(quartet(a, b, a, b))
+            # the reference turns numpy FP warnings into exceptions globally at import
+            # (hf_extensions/diis.py:5); far-apart pairs underflow harmlessly
+            with np.errstate(all="ignore"):
+                blk = np.asarray(quartet(a, b, a, b))
             na, nb = blk.shape[0], blk.shape[1]
-            bound_cache[(a, b)] = max(np.sqrt(abs(blk[m, n, m, n])) for m in range(na) for n in range(nb))
+            bound_cache[(a, b)] = float(max(np.sqrt(abs(blk[m, n, m, n])) for m in range(na) for n in range(nb)))
         return bound_cache[(a, b)]
 
     # seeded sample of unique pair-of-pairs; screening with the reference's own test
     # (hartree_fock.py:293-294).  Bounds are computed (untimed) with the same reference code.
     sample = []
     tries = 0
-    while len(sample) < 4000 and tries < 200000:
+    while len(sample) < 40000 and tries < 2000000:
         tries += 1
         a, b, c, d = (int(x) for x in rng.integers(0, nshell, 4))
         a, b = min(a, b), max(a, b)
         c, d = min(c, d), max(c, d)
-        if bound(a, b) * bound(c, d) > THRESH:
+        if float(bound(a, b)) * float(bound(c, d)) > THRESH:
             sample.append((a, b, c, d))
-        if time.time() - t_build0 > 3 * seconds:
+        if time.time() - t_build0 > 2 * seconds and len(sample) >= 500:
             break
     t0 = time.perf_counter()
     n_eri = 0
     n_q = 0
-    for (a, b, c, d) in sample:
-        blk = quartet(a, b, c, d)
-        n_eri += int(np.asarray(blk).size)
-        n_q += 1
-        if time.perf_counter() - t0 > seconds:
-            break
+    done = False
+    while not done:                     # cycle through the sample until the time budget is used
+        for (a, b, c, d) in sample:
+            with np.errstate(all="ignore"):
+                blk = quartet(a, b, c, d)
+            n_eri += int(np.asarray(blk).size)
+            n_q += 1
+            if time.perf_counter() - t0 > seconds:
+                done = True
+                break
     dt = time.perf_counter() - t0
     return {"value": n_eri / dt, "unit": UNIT, "cores": 1, "kind": kind,
-            "sample": "%d surviving unique shell quartets (%d ERIs) drawn uniformly (seed %d) from the "
+            "sample": "%d evaluations of surviving unique shell quartets (%d ERIs) drawn uniformly (seed %d) from the "
                       "(H2O)%d 6-31G** quartet list, %s two_electron per quartet, %.1f s on 1 core; "
                       "survival rate of the draw %.3f"
                       % (n_q, n_eri, seed, n_waters,

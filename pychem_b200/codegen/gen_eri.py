@@ -323,6 +323,8 @@ class ClassGen:
         s.append("  int i, j;")
         s.append("  if (!pc_decode_task(A, t, i, j)) return;")
         s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = A.bra.K, KK = A.ket.K;")
+        s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
+        s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(A.bra.fx + i), __ldg(A.bra.fy + i), __ldg(A.ket.fx + j), __ldg(A.ket.fy + j));" % (NA, NB, NC, ND))
         s.append("  const double AB0 = __ldg(A.bra.xy + i), AB1 = __ldg(A.bra.xy + nb + i), AB2 = __ldg(A.bra.xy + 2 * nb + i);")
         s.append("  const double CD0 = __ldg(A.ket.xy + j), CD1 = __ldg(A.ket.xy + nk + j), CD2 = __ldg(A.ket.xy + 2 * nk + j);")
         s.append("  double acc[NE * NF];")
