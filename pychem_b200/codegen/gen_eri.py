@@ -320,8 +320,8 @@ class ClassGen:
         s.append("template <int MODE>")
         s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const PcEriArgs A) {" % (block, self.min_blocks(), self.name))
         s.append("  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
-        s.append("  int i, j;")
-        s.append("  if (!pc_decode_task(A, t, i, j)) return;")
+        s.append("  int i, j, seg_lo, seg_hi;")
+        s.append("  if (!pc_decode_task(A, t, i, j, seg_lo, seg_hi)) return;")
         s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = A.bra.K, KK = A.ket.K;")
         s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
         s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(A.bra.fx + i), __ldg(A.bra.fy + i), __ldg(A.ket.fx + j), __ldg(A.ket.fy + j));" % (NA, NB, NC, ND))
@@ -340,7 +340,7 @@ class ClassGen:
         s.append("  double g[NSPH];")
         for line in tail:
             s.append("  " + line)
-        s.append("  pc_epilogue<MODE, %d, %d, %d, %d>(A, t, i, j, g);" % (NA, NB, NC, ND))
+        s.append("  pc_epilogue<MODE, %d, %d, %d, %d>(A, t, i, j, seg_lo, seg_hi, g);" % (NA, NB, NC, ND))
         s.append("}")
         s.append("}  // namespace")
         s.append("")

@@ -76,6 +76,10 @@ struct HostPair {
 struct Kind {
   int lx, ly, K, pc;
   std::vector<int> pairs;  // pair ids in bucket order
+  // after pc_schwarz the bucket is ordered in GROUPS of pairs sharing their primary shell x,
+  // groups by descending group maximum, pairs inside a group by descending Schwarz maximum
+  std::vector<int> gstart;      // [ngroups + 1] first position of every group
+  std::vector<double> pm;       // [n] Schwarz maximum by position
   DevBuf<int> fx, fy, pid;
   DevBuf<double> xy, prim;
   PcPairKind view() const {
@@ -92,8 +96,10 @@ struct PlanItem {
   int same;
   long long total;      // all tasks of the bucket pair
   long long begin, count;  // this rank's slice
-  DevBuf<long long>* off;
-  DevBuf<int>* blk_i0;
+  int nseg;
+  DevBuf<long long>* seg_off;
+  DevBuf<int>* seg_ij;     // int2 per segment
+  DevBuf<int>* warp_s0;
 };
 
 bool is_device_ptr(const void* p) {
@@ -503,10 +509,34 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax) {
         p.pmax = mx;
       }
     }
-    // sort every bucket by descending Schwarz maximum and rebuild its tables
+    // order every bucket in groups of pairs sharing the primary shell x (groups by descending
+    // group maximum, pairs inside a group by descending Schwarz maximum) and rebuild its tables.
+    // Consecutive tasks of one bra pair then share the ket's primary shell c, so the lanes of a
+    // warp hit the same K[a,c] / K[b,c] / J[a,b] addresses and can be reduced by shuffles; inside
+    // a group the survivors of a bra pair are still a prefix.
     for (Kind* k : h->kinds) {
-      std::stable_sort(k->pairs.begin(), k->pairs.end(),
-                       [&](int p, int q) { return h->pairs[p].pmax > h->pairs[q].pmax; });
+      std::map<int, double> gmax;
+      for (int p : k->pairs) {
+        double& g = gmax[h->pairs[p].x];
+        g = std::max(g, h->pairs[p].pmax);
+      }
+      std::stable_sort(k->pairs.begin(), k->pairs.end(), [&](int p, int q) {
+        const HostPair& P = h->pairs[p];
+        const HostPair& Q = h->pairs[q];
+        if (P.x != Q.x) {
+          const double gp = gmax[P.x], gq = gmax[Q.x];
+          if (gp != gq) return gp > gq;
+          return P.x < Q.x;
+        }
+        return P.pmax > Q.pmax;
+      });
+      k->gstart.clear();
+      k->pm.resize(k->pairs.size());
+      for (size_t i = 0; i < k->pairs.size(); ++i) {
+        k->pm[i] = h->pairs[k->pairs[i]].pmax;
+        if (i == 0 || h->pairs[k->pairs[i]].x != h->pairs[k->pairs[i - 1]].x) k->gstart.push_back((int)i);
+      }
+      k->gstart.push_back((int)k->pairs.size());
       if (upload_kind(h, k)) return 1;
     }
     h->schwarz_done = true;
@@ -531,6 +561,8 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     for (auto* b : h->plan_ibufs) delete b;
     h->plan_ibufs.clear();
     h->plan.clear();
+    std::vector<long long> seg_off;
+    std::vector<int> seg_i, seg_j0;
     h->my_quartets = h->my_eris = h->all_quartets = h->all_eris = 0;
     const int nk = (int)h->kinds.size();
     for (int ka = 0; ka < nk; ++ka)
@@ -540,42 +572,70 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         const Kind* B = h->kinds[kb];
         const Kind* Kt = h->kinds[kk];
         const int same = (kb == kk);
-        const int nb = (int)B->pairs.size(), nkk = (int)Kt->pairs.size();
-        std::vector<long long> off(nb + 1, 0);
-        // kets sorted by descending pmax: survivors of bra i are a prefix [0, cut)
-        // test is the reference's: max(B_ab)*max(B_cd) > thresh, strict (hartree_fock.py:293-294)
-        int cut = nkk;
+        const int nb = (int)B->pairs.size();
+        const int ng = (int)Kt->gstart.size() - 1;
+        // segments: (bra pair i) x (prefix of one ket group).  The test is the reference's:
+        // max(B_ab)*max(B_cd) > thresh, strict (hartree_fock.py:293-294); unique quartets only
+        // (ket position >= bra position inside one bucket); the diagonal (ab|ab) is always kept
+        // (hartree_fock.py:244-250).
+        seg_off.assign(1, 0);
+        seg_i.clear();
+        seg_j0.clear();
         for (int i = 0; i < nb; ++i) {
-          const double pb = h->pairs[B->pairs[i]].pmax;
-          while (cut > 0 && !(pb * h->pairs[Kt->pairs[cut - 1]].pmax > thresh)) --cut;
-          long long cnt;
-          if (same) cnt = std::max(cut - i, 1);   // diagonal (ab|ab) always kept (hartree_fock.py:244-250)
-          else cnt = cut;
-          off[i + 1] = off[i] + cnt;
+          const double pb = B->pm[i];
+          bool diag = !same;
+          for (int g = 0; g < ng; ++g) {
+            const int gs = Kt->gstart[g], ge = Kt->gstart[g + 1];
+            if (!(pb * Kt->pm[gs] > thresh)) break;       // groups are ordered by their maximum
+            int lo = gs, hi = ge;                          // first position that fails the test
+            while (hi - lo > 1) {
+              const int mid = (lo + hi) >> 1;
+              if (pb * Kt->pm[mid] > thresh) lo = mid; else hi = mid;
+            }
+            int j0 = gs;
+            const int j1 = hi;
+            if (same) j0 = std::max(j0, i);
+            if (j1 <= j0) continue;
+            if (same && i >= j0 && i < j1) diag = true;
+            seg_i.push_back(i);
+            seg_j0.push_back(j0);
+            seg_off.push_back(seg_off.back() + (j1 - j0));
+          }
+          if (!diag) {
+            seg_i.push_back(i);
+            seg_j0.push_back(i);
+            seg_off.push_back(seg_off.back() + 1);
+          }
         }
-        const long long total = off[nb];
+        const long long total = seg_off.back();
         if (total == 0) continue;
         PlanItem it;
         it.kb = kb; it.kk = kk; it.same = same; it.total = total;
         it.begin = total * rank / nranks;
         it.count = total * (rank + 1) / nranks - it.begin;
-        it.off = new DevBuf<long long>();
-        h->plan_bufs.push_back(it.off);
-        PC_CUDA(it.off->upload(off, h->stream));
+        it.nseg = (int)seg_i.size();
+        it.seg_off = new DevBuf<long long>();
+        h->plan_bufs.push_back(it.seg_off);
+        it.seg_ij = new DevBuf<int>();
+        it.warp_s0 = new DevBuf<int>();
+        h->plan_ibufs.push_back(it.seg_ij);
+        h->plan_ibufs.push_back(it.warp_s0);
+        PC_CUDA(it.seg_off->upload(seg_off, h->stream));
+        std::vector<int> ij(2 * seg_i.size());
+        for (size_t k = 0; k < seg_i.size(); ++k) { ij[2 * k] = seg_i[k]; ij[2 * k + 1] = seg_j0[k]; }
+        PC_CUDA(it.seg_ij->upload(ij, h->stream));
+        std::vector<int> s0;
         {
-          // bra pair of every block's first task (block size is a property of the class kernel)
-          const int bs = pc_block_table[B->pc][Kt->pc];
-          const long long nblk = (it.count + bs - 1) / bs;
-          std::vector<int> i0((size_t)nblk);
+          // segment of every warp's first task
+          const long long nwarp = (it.count + 31) / 32;
+          s0.resize((size_t)nwarp);
           int cur = 0;
-          for (long long b = 0; b < nblk; ++b) {
-            const long long g0 = it.begin + b * bs;
-            while (off[cur + 1] <= g0) ++cur;
-            i0[(size_t)b] = cur;
+          for (long long w = 0; w < nwarp; ++w) {
+            const long long g0 = it.begin + w * 32;
+            while (seg_off[cur + 1] <= g0) ++cur;
+            s0[(size_t)w] = cur;
           }
-          it.blk_i0 = new DevBuf<int>();
-          h->plan_ibufs.push_back(it.blk_i0);
-          PC_CUDA(it.blk_i0->upload(i0, h->stream));
+          PC_CUDA(it.warp_s0->upload(s0, h->stream));
         }
         PC_CUDA(cudaStreamSynchronize(h->stream));
         const long long nsph = (long long)(2 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
@@ -677,7 +737,8 @@ int pc_eri_tensor(pc_basis* h, double* G_dev, double* G_host) {
   for (const PlanItem& it : h->plan) {
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.off = it.off->p; A.blk_i0 = it.blk_i0->p; A.same_kind = it.same; A.t_begin = it.begin; A.t_count = it.count;
+    A.seg_off = it.seg_off->p; A.seg_ij = (const int2*)it.seg_ij->p; A.warp_s0 = it.warp_s0->p;
+    A.nseg = it.nseg; A.t_begin = it.begin; A.t_count = it.count;
     A.G = G_dev;
     if (launch_class(h, PC_MODE_TENSOR, h->kinds[it.kb], h->kinds[it.kk], A)) return 1;
   }
@@ -767,7 +828,8 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
     if (it.count == 0) continue;
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.off = it.off->p; A.blk_i0 = it.blk_i0->p; A.same_kind = it.same; A.t_begin = it.begin; A.t_count = it.count;
+    A.seg_off = it.seg_off->p; A.seg_ij = (const int2*)it.seg_ij->p; A.warp_s0 = it.warp_s0->p;
+    A.nseg = it.nseg; A.t_begin = it.begin; A.t_count = it.count;
     A.Dj = dt; A.Da = da; A.Db = db;
     A.Jacc = acc_dev; A.Kaacc = acc_dev + nn; A.Kbacc = acc_dev + 2 * nn;
     A.out = acc_dev;
