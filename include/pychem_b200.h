@@ -21,6 +21,7 @@ extern "C" {
 typedef struct pc_basis pc_basis; /* opaque: shell table, shell-pair tables, Boys table, plans */
 
 /* digestion variants for pc_jk_* (what make_coulomb_exchange_matrices is asked to do) */
+#define PC_JK_AUTO 0 /* pc_jk_direct only: classify the densities on the device, pick the cheapest exact variant */
 #define PC_JK_RHF 2 /* symmetric densities, D_alpha == D_beta (one exchange matrix computed)      */
 #define PC_JK_UHF 3 /* symmetric densities, two spins                                             */
 #define PC_JK_GEN 4 /* general non-symmetric densities (NOCI co-densities, Methods/noci.py:204-211) */
@@ -112,6 +113,9 @@ int pc_jk_finalize(pc_basis* h, int variant, const double* acc_dev, double* J, d
                    double* Xb);
 int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
                  double* J, double* Xa, double* Xb);
+/* variant (PC_JK_RHF/UHF/GEN) the densities allow: symmetric & Da==Db / symmetric / general.
+ * Exact element-wise tests on the device; host or device inputs. */
+int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double* Db, int* variant);
 
 /*
  * Measurement hooks (bench.py): with profiling on, pc_jk_direct_accumulate brackets every plan

@@ -258,21 +258,19 @@ class ClassGen:
     def prim_prologue(self, s, nmax):
         """Primitive loops: ket primitives outside (per-lane, coalesced loads, once per ket
         primitive), bra primitives inside (warp-uniform addresses -> broadcast loads)."""
-        s.append("  const double* __restrict__ bp = A.bra.prim + i;")
-        s.append("  const double* __restrict__ kp = A.ket.prim + j;")
-        s.append("  const size_t sb = (size_t)KB * nb, sk = (size_t)KK * nk;")
-        s.append("  for (int ik = 0; ik < KK; ++ik) {")
-        s.append("    const double sQ = __ldg(kp + (size_t)ik * nk), UQ = __ldg(kp + sk + (size_t)ik * nk);")
-        s.append("    const double Qx = __ldg(kp + 2 * sk + (size_t)ik * nk), Qy = __ldg(kp + 3 * sk + (size_t)ik * nk), Qz = __ldg(kp + 4 * sk + (size_t)ik * nk);")
-        s.append("    const double kzQ = __ldg(kp + 5 * sk + (size_t)ik * nk);")
+        s.append("  const double2* __restrict__ bp = reinterpret_cast<const double2*>(A.bra.prim) + i;")
+        s.append("  const double2* __restrict__ kp = reinterpret_cast<const double2*>(A.ket.prim) + j;")
+        s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
+        s.append("    const double2 q0 = __ldg(kp), q1 = __ldg(kp + nk), q2 = __ldg(kp + 2 * (size_t)nk);")
+        s.append("    const double sQ = q0.x, UQ = q0.y, Qx = q1.x, Qy = q1.y, Qz = q2.x, kzQ = q2.y;")
         s.append("    const double eta = 0.5 * sQ;")
         s.append("    const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;")
         for n in range(1, nmax + 1):
             s.append("    const double ne%d = %d.0 * eta;" % (n, n))
-        s.append("    for (int ib = 0; ib < KB; ++ib) {")
-        s.append("      const double sP = __ldg(bp + (size_t)ib * nb), UP = __ldg(bp + sb + (size_t)ib * nb);")
-        s.append("      const double Px = __ldg(bp + 2 * sb + (size_t)ib * nb), Py = __ldg(bp + 3 * sb + (size_t)ib * nb), Pz = __ldg(bp + 4 * sb + (size_t)ib * nb);")
-        s.append("      const double kzP = __ldg(bp + 5 * sb + (size_t)ib * nb);")
+        s.append("    const double2* __restrict__ bq = bp;")
+        s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
+        s.append("      const double2 p0 = __ldg(bq), p1 = __ldg(bq + nb), p2 = __ldg(bq + 2 * (size_t)nb);")
+        s.append("      const double sP = p0.x, UP = p0.y, Px = p1.x, Py = p1.y, Pz = p2.x, kzP = p2.y;")
         s.append("      const double zeta = 0.5 * sP;")
         s.append("      const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;")
         s.append("      const double R0 = Px - Qx, R1 = Py - Qy, R2_ = Pz - Qz;")

@@ -226,6 +226,21 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, const double* __r
   }
 }
 
+// flags |= 1 if any of Dt, Da, Db is not symmetric; flags |= 2 if Da != Db (bitwise compare of
+// values, the same test the host mirror would make with numpy.array_equal)
+__global__ void classify_kernel(int N, const double* __restrict__ Dt, const double* __restrict__ Da,
+                                const double* __restrict__ Db, int* flags) {
+  const size_t nn = (size_t)N * N;
+  int f = 0;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < nn;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = idx / N, c = idx % N, tr = c * N + r;
+    if (r < c && (Dt[idx] != Dt[tr] || Da[idx] != Da[tr] || Db[idx] != Db[tr])) f |= 1;
+    if (Da[idx] != Db[idx]) f |= 2;
+  }
+  if (f) atomicOr(flags, f);
+}
+
 // register-resident DFMA loop: 8 independent chains per thread
 __global__ void dfma_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5,
@@ -266,6 +281,7 @@ struct pc_basis {
   long long my_quartets = 0, my_eris = 0, all_quartets = 0, all_eris = 0;
   // scratch
   DevBuf<double> acc, dstage, ostage;
+  DevBuf<int> flags;
   long long launches = 0;
   // side streams: the (bra bucket, ket bucket) launches of one Fock build are independent
   // (they only meet in the atomics), so they are spread round-robin to overlap their tails
@@ -326,11 +342,16 @@ int upload_kind(pc_basis* h, Kind* k) {
         const double sigma = 1.0 / (a + b);
         const double U = std::pow(M_PI * sigma, 1.5) * std::exp(-a * b * sigma * r2);
         const double cc = h->scc[X.poff + ia] * h->scc[Y.poff + ib];
-        prim[((size_t)0 * K + q) * n + i] = sigma;
-        prim[((size_t)1 * K + q) * n + i] = U * cc * cn;
-        for (int c = 0; c < 3; ++c)
-          prim[((size_t)(2 + c) * K + q) * n + i] = (a * X.A[c] + b * Y.A[c]) * sigma;
-        prim[((size_t)5 * K + q) * n + i] = b * sigma;  // kappa*zeta = (2b)(sigma/2)
+        // [K][3][n] double2: {sigma, U}, {Px, Py}, {Pz, kz}: three 16-byte loads per primitive pair
+        double* o0 = &prim[(((size_t)q * 3 + 0) * n + i) * 2];
+        double* o1 = &prim[(((size_t)q * 3 + 1) * n + i) * 2];
+        double* o2 = &prim[(((size_t)q * 3 + 2) * n + i) * 2];
+        o0[0] = sigma;
+        o0[1] = U * cc * cn;
+        o1[0] = (a * X.A[0] + b * Y.A[0]) * sigma;
+        o1[1] = (a * X.A[1] + b * Y.A[1]) * sigma;
+        o2[0] = (a * X.A[2] + b * Y.A[2]) * sigma;
+        o2[1] = b * sigma;  // kappa*zeta = (2b)(sigma/2)
       }
   }
   PC_CUDA(k->fx.upload(fx, h->stream));
@@ -359,7 +380,7 @@ int launch_class(pc_basis* h, int mode, const Kind* kb, const Kind* kk, PcEriArg
 
 // copy a host-or-device N*N matrix into device staging (returns device pointer)
 int stage_in(pc_basis* h, const double* src, double* stage, const double** out) {
-  if (is_device_ptr(src)) {
+  if (src == stage || is_device_ptr(src)) {
     *out = src;
     return 0;
   }
@@ -898,11 +919,41 @@ int pc_jk_finalize(pc_basis* h, int variant, const double* acc_dev, double* J, d
   return 0;
 }
 
+int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double* Db, int* variant) {
+  if (!h || !Dt || !Da || !variant) return fail("pc_jk_classify: null");
+  PC_CUDA(cudaSetDevice(h->device));
+  if (ensure_scratch(h)) return 1;
+  if (!Db) Db = Da;
+  const size_t nn = (size_t)h->nbf * h->nbf;
+  const double *dt, *da, *db;
+  if (stage_in(h, Dt, h->dstage.p, &dt) || stage_in(h, Da, h->dstage.p + nn, &da) ||
+      stage_in(h, Db, h->dstage.p + 2 * nn, &db)) return 1;
+  if (!h->flags.p) PC_CUDA(h->flags.alloc(1));
+  PC_CUDA(cudaMemsetAsync(h->flags.p, 0, sizeof(int), h->stream));
+  const int blocks = (int)std::min<size_t>((nn + 255) / 256, 148 * 8);
+  classify_kernel<<<blocks, 256, 0, h->stream>>>(h->nbf, dt, da, db, h->flags.p);
+  PC_CUDA(cudaGetLastError());
+  h->launches += 1;
+  int f = 0;
+  PC_CUDA(cudaMemcpyAsync(&f, h->flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PC_CUDA(cudaStreamSynchronize(h->stream));
+  *variant = (f & 1) ? PC_JK_GEN : ((f & 2) ? PC_JK_UHF : PC_JK_RHF);
+  return 0;
+}
+
 int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
                  double* J, double* Xa, double* Xb) {
   if (!h) return fail("pc_jk_direct: null");
   PC_CUDA(cudaSetDevice(h->device));
   if (ensure_scratch(h)) return 1;
+  if (variant == PC_JK_AUTO) {
+    // classify on the device, then digest straight from the staged copies (no second upload)
+    if (pc_jk_classify(h, Dt, Da, Db, &variant)) return 1;
+    const size_t nn = (size_t)h->nbf * h->nbf;
+    if (!is_device_ptr(Dt)) Dt = h->dstage.p;
+    if (!is_device_ptr(Da)) Da = h->dstage.p + nn;
+    if (Db && !is_device_ptr(Db)) Db = h->dstage.p + 2 * nn;
+  }
   if (pc_jk_direct_accumulate(h, variant, Dt, Da, Db, h->acc.p)) return 1;
   return pc_jk_finalize(h, variant, h->acc.p, J, Xa, Xb);
 }

@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from .basis_table import BasisTable
 
-RHF, UHF, GEN = 2, 3, 4           # PC_JK_* in include/pychem_b200.h
+AUTO, RHF, UHF, GEN = 0, 2, 3, 4  # PC_JK_* in include/pychem_b200.h
 INTEGRAL_THRESHOLD = 1.0e-8        # Data/constants.py:31
 
 
@@ -162,7 +162,10 @@ class DeviceBasis:
     def _outputs(self, like):
         N = self.nbf
         if isinstance(like, np.ndarray):
-            return [np.empty((N, N)) for _ in range(3)]
+            # page-locked result arrays: the device->host copies run at full PCIe rate
+            # (numpy views of pinned torch storage; torch's caching host allocator recycles them)
+            import torch
+            return [torch.empty((N, N), dtype=torch.float64, pin_memory=True).numpy() for _ in range(3)]
         import torch
         return [torch.empty((N, N), dtype=torch.float64, device=like.device) for _ in range(3)]
 
@@ -184,10 +187,15 @@ class DeviceBasis:
         """Integral-direct J/K.  With an initialised torch.distributed process group and a plan
         built with nranks>1, partial accumulators are summed with one NCCL all-reduce."""
         Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
-        if variant is None:
-            variant = classify_densities(Dt, Da, Db) if isinstance(Dt, np.ndarray) else GEN
         if self.counts is None:
             self.plan()
+        if variant is None:
+            if self.counts["nranks"] == 1:
+                variant = AUTO                      # classified on the device inside pc_jk_direct
+            else:
+                v = ctypes.c_int()
+                _lib.check(self.lib.pc_jk_classify(self.h, _ptr(Dt), _ptr(Da), _ptr(Db), ctypes.byref(v)))
+                variant = v.value
         J, Xa, Xb = self._outputs(Dt)
         if self.counts["nranks"] == 1:
             _lib.check(self.lib.pc_jk_direct(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db),
