@@ -271,6 +271,9 @@ def run_b200(args):
     import torch.distributed as dist
     from pychem_b200 import dist as pdist, engine, hartree_fock as hf_gpu, structures as S
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the ONE JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, world, local = pdist.init("nccl" if args.gpus > 1 else None)
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
