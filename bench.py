@@ -245,25 +245,33 @@ class _State:
 
 
 def algorithmic_flops(db, variant):
-    """Flops of one Fock build for THIS rank's slice and for all ranks: SURVEY 8(d) model."""
+    """Flops of one Fock build, SURVEY 8(d) model (pychem_b200/data/flop_model.json):
+    primitive quartets * flop_prim + quartets * (flop_cont + digestion).  `executed` counts the
+    primitive quartets the kernels actually visit (after the primitive-pair cut-off); `reference`
+    counts every primitive quartet the reference would loop over (K_a K_b K_c K_d per quartet).
+    The roofline fraction is computed from `executed` (the conservative one)."""
     with open(os.path.join(ROOT, "pychem_b200", "data", "flop_model.json")) as fh:
         model = json.load(fh)
     cls, kprim, tasks, ms = db.plan_items()
+    prim_exec = db.prim_exec
     names = "spd"
     digest_fma = {2: 2 + 4, 3: 2 + 8, 4: 2 + 16}[variant]       # J + K updates per ERI value
-    mine = total = 0.0
+    mine = total = total_ref = 0.0
     per_class = {}
-    for (l1, l2, l3, l4), (kb, kk), (tot, cnt), t in zip(cls, kprim, tasks, ms):
+    for (l1, l2, l3, l4), (kb, kk), (tot, cnt), t, pe in zip(cls, kprim, tasks, ms, prim_exec):
         name = names[l1] + names[l2] + names[l3] + names[l4]
         m = model[name]
-        per_q = kb * kk * m["flop_prim"] + m["flop_cont"] + 2 * digest_fma * m["nsph"]
-        mine += per_q * cnt
-        total += per_q * tot
+        per_q = m["flop_cont"] + 2 * digest_fma * m["nsph"]
+        f_tot = pe * m["flop_prim"] + per_q * tot
+        share = cnt / tot if tot else 0.0
+        mine += f_tot * share
+        total += f_tot
+        total_ref += (kb * kk * m["flop_prim"] + per_q) * tot
         e = per_class.setdefault(name, {"flops": 0.0, "ms": 0.0, "quartets": 0})
-        e["flops"] += per_q * cnt
+        e["flops"] += f_tot * share
         e["ms"] += float(t)
         e["quartets"] += int(cnt)
-    return mine, total, per_class
+    return mine, total, per_class, total_ref
 
 
 def run_b200(args):
@@ -368,7 +376,7 @@ def run_b200(args):
     db.set_profiling(True)
     _lib.check(lib.pc_jk_direct_accumulate(db.h, variant, P(Dt_d), P(Da_d), P(Da_d), P(acc)))
     db.set_profiling(False)
-    my_flops, all_flops, per_class = algorithmic_flops(db, variant)
+    my_flops, all_flops, per_class, ref_flops = algorithmic_flops(db, variant)
     peak = engine.fp64_peak_tflops(local)
     top = max(per_class.items(), key=lambda kv: kv[1]["ms"])
     eri_ms = sum(v["ms"] for v in per_class.values())
@@ -383,7 +391,11 @@ def run_b200(args):
                                     "share_of_step": top[1]["ms"] / ms_step,
                                     "achieved": top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 if top[1]["ms"] else None,
                                     "frac": (top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 / peak) if top[1]["ms"] and peak else None},
-                "algorithmic_gflop_per_step": all_flops / 1e9}
+                "algorithmic_gflop_per_step": all_flops / 1e9,
+                "reference_unscreened_gflop_per_step": ref_flops / 1e9,
+                "flop_count": "executed primitive quartets (after the 1e-24 primitive-pair cut-off) * flop_prim "
+                              "+ quartets * (flop_cont + digestion); the reference's unscreened primitive "
+                              "loops would be reference_unscreened_gflop_per_step"}
     # pure ERI generation (same schedule, integrals discarded): the "FP64 ERIs/sec" of generation
     def step_eri_only():
         _lib.check(lib.pc_jk_direct_accumulate(db.h, 5, P(Dt_d), P(Da_d), P(Da_d), P(acc)))

@@ -122,11 +122,13 @@ int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double
  * item (one kernel launch per (bra bucket, ket bucket)) with CUDA events on the launching stream
  * and synchronises at the end.  pc_plan_items reports, per item k: cls[4k..] = (lx1,ly1,lx2,ly2),
  * kprim[2k..] = primitive pairs per bra/ket shell pair, tasks[2k..] = (all quartets, this rank's
- * quartets), ms[k] = device time of the item in the last profiled accumulate.  Arrays may be NULL.
+ * quartets), ms[k] = device time of the item in the last profiled accumulate, prim_exec[k] =
+ * primitive quartets the whole bucket pair actually visits (after the primitive-pair cut-off;
+ * kprim gives the unscreened contraction depths the reference loops over).  Arrays may be NULL.
  */
 int pc_set_profiling(pc_basis* h, int on);
 int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim,
-                  long long* tasks, float* ms);
+                  long long* tasks, float* ms, double* prim_exec);
 
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int pc_launch_count(const pc_basis* h, long long* n);

@@ -33,7 +33,7 @@ SIGNATURES = {
     "pc_jk_classify": [c_vp, c_vp, c_vp, c_vp, c_ip],
     "pc_launch_count": [c_vp, c_llp],
     "pc_set_profiling": [c_vp, ctypes.c_int],
-    "pc_plan_items": [c_vp, ctypes.c_int, c_ip, c_ip, c_ip, c_llp, ctypes.POINTER(ctypes.c_float)],
+    "pc_plan_items": [c_vp, ctypes.c_int, c_ip, c_ip, c_ip, c_llp, ctypes.POINTER(ctypes.c_float), c_dp],
     "pc_fp64_peak": [ctypes.c_int, c_dp],
 }
 

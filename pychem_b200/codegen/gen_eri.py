@@ -320,7 +320,8 @@ class ClassGen:
         s.append("  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
         s.append("  int i, j, seg_lo, seg_hi;")
         s.append("  if (!pc_decode_task(A, t, i, j, seg_lo, seg_hi)) return;")
-        s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = A.bra.K, KK = A.ket.K;")
+        s.append("  // contraction depths after the primitive-pair cut-off (per shell pair)")
+        s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = __ldg(A.bra.keff + i), KK = __ldg(A.ket.keff + j);")
         s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
         s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(A.bra.fx + i), __ldg(A.bra.fy + i), __ldg(A.ket.fx + j), __ldg(A.ket.fy + j));" % (NA, NB, NC, ND))
         s.append("  const double AB0 = __ldg(A.bra.xy + i), AB1 = __ldg(A.bra.xy + nb + i), AB2 = __ldg(A.bra.xy + 2 * nb + i);")

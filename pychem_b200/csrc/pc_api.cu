@@ -57,6 +57,8 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
 };
 
+constexpr double PC_PRIM_EPS = 1.0e-24;   // primitive-pair prefactor cut-off (see upload_kind)
+
 inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
 inline int pair_class(int lx, int ly) { return lx * (lx + 1) / 2 + ly; }  // ss ps pp ds dp dd
 
@@ -80,13 +82,14 @@ struct Kind {
   // groups by descending group maximum, pairs inside a group by descending Schwarz maximum
   std::vector<int> gstart;      // [ngroups + 1] first position of every group
   std::vector<double> pm;       // [n] Schwarz maximum by position
-  DevBuf<int> fx, fy, pid;
+  std::vector<int> keff_h;      // [n] significant primitive pairs by position
+  DevBuf<int> fx, fy, pid, keff;
   DevBuf<double> xy, prim;
   PcPairKind view() const {
     PcPairKind v;
     v.n = (int)pairs.size();
     v.K = K;
-    v.fx = fx.p; v.fy = fy.p; v.pid = pid.p; v.xy = xy.p; v.prim = prim.p;
+    v.fx = fx.p; v.fy = fy.p; v.pid = pid.p; v.keff = keff.p; v.xy = xy.p; v.prim = prim.p;
     return v;
   }
 };
@@ -96,6 +99,7 @@ struct PlanItem {
   int same;
   long long total;      // all tasks of the bucket pair
   long long begin, count;  // this rank's slice
+  double prim_exec;        // primitive quartets actually visited by the whole bucket pair
   int nseg;
   DevBuf<long long>* seg_off;
   DevBuf<int>* seg_ij;     // int2 per segment
@@ -328,7 +332,7 @@ namespace {
 int upload_kind(pc_basis* h, Kind* k) {
   const int n = (int)k->pairs.size();
   const int K = k->K;
-  std::vector<int> fx(n), fy(n), pid(n);
+  std::vector<int> fx(n), fy(n), pid(n), keff(n);
   std::vector<double> xy((size_t)3 * n), prim((size_t)6 * K * n);
   // uniform normalisation constants folded into the pair prefactor (structures.py:850-856):
   // s: pi^-3/4, p: sqrt(2) pi^-3/4, d: 2 pi^-3/4 (the xy-type d component; xx-type ratio 1/sqrt3
@@ -351,25 +355,40 @@ int upload_kind(pc_basis* h, Kind* k) {
       r2 += d * d;
     }
     const double cn = lnorm[X.l] * lnorm[Y.l] * pf_half;
-    int q = 0;
+    // primitive pairs of this shell pair, most significant first.  Pairs whose prefactor
+    // U*cc is below PC_PRIM_EPS contribute < 1e-20 to any integral (two-centre pairs of tight
+    // primitives: U = exp(-ab/(a+b) r^2) underflows) and are cut off by keff.  The reference
+    // visits them all (no primitive screening); the results differ by < 1e-16.
+    struct PP { double sigma, ucc, P[3], kz; };
+    std::vector<PP> pp;
+    pp.reserve(K);
     for (int ia = 0; ia < X.K; ++ia)
-      for (int ib = 0; ib < Y.K; ++ib, ++q) {
+      for (int ib = 0; ib < Y.K; ++ib) {
         const double a = h->exps[X.poff + ia], b = h->exps[Y.poff + ib];
-        const double sigma = 1.0 / (a + b);
-        const double U = std::pow(M_PI * sigma, 1.5) * std::exp(-a * b * sigma * r2);
-        const double cc = h->scc[X.poff + ia] * h->scc[Y.poff + ib];
-        // [K][3][n] double2: {sigma, U}, {Px, Py}, {Pz, kz}: three 16-byte loads per primitive pair
-        double* o0 = &prim[(((size_t)q * 3 + 0) * n + i) * 2];
-        double* o1 = &prim[(((size_t)q * 3 + 1) * n + i) * 2];
-        double* o2 = &prim[(((size_t)q * 3 + 2) * n + i) * 2];
-        o0[0] = sigma;
-        o0[1] = U * cc * cn;
-        o1[0] = (a * X.A[0] + b * Y.A[0]) * sigma;
-        o1[1] = (a * X.A[1] + b * Y.A[1]) * sigma;
-        o2[0] = (a * X.A[2] + b * Y.A[2]) * sigma;
-        o2[1] = b * sigma;  // kappa*zeta = (2b)(sigma/2)
+        PP e;
+        e.sigma = 1.0 / (a + b);
+        const double U = std::pow(M_PI * e.sigma, 1.5) * std::exp(-a * b * e.sigma * r2);
+        e.ucc = U * h->scc[X.poff + ia] * h->scc[Y.poff + ib] * cn;
+        for (int c = 0; c < 3; ++c) e.P[c] = (a * X.A[c] + b * Y.A[c]) * e.sigma;
+        e.kz = b * e.sigma;  // kappa*zeta = (2b)(sigma/2)
+        pp.push_back(e);
       }
+    std::stable_sort(pp.begin(), pp.end(), [](const PP& u, const PP& v) { return std::fabs(u.ucc) > std::fabs(v.ucc); });
+    int ke = 0;
+    while (ke < K && std::fabs(pp[ke].ucc) >= PC_PRIM_EPS) ++ke;
+    keff[i] = std::max(ke, 1);
+    for (int q = 0; q < K; ++q) {
+      // [K][3][n] double2: {sigma, U}, {Px, Py}, {Pz, kz}: three 16-byte loads per primitive pair
+      double* o0 = &prim[(((size_t)q * 3 + 0) * n + i) * 2];
+      double* o1 = &prim[(((size_t)q * 3 + 1) * n + i) * 2];
+      double* o2 = &prim[(((size_t)q * 3 + 2) * n + i) * 2];
+      o0[0] = pp[q].sigma; o0[1] = pp[q].ucc;
+      o1[0] = pp[q].P[0];  o1[1] = pp[q].P[1];
+      o2[0] = pp[q].P[2];  o2[1] = pp[q].kz;
+    }
   }
+  k->keff_h = keff;
+  PC_CUDA(k->keff.upload(keff, h->stream));
   PC_CUDA(k->fx.upload(fx, h->stream));
   PC_CUDA(k->fy.upload(fy, h->stream));
   PC_CUDA(k->pid.upload(pid, h->stream));
@@ -646,7 +665,18 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         }
         const long long total = seg_off.back();
         if (total == 0) continue;
+        // executed primitive quartets: sum over segments of keff(bra) * sum keff(kets)
+        double prim_exec = 0;
+        {
+          std::vector<double> pre(Kt->keff_h.size() + 1, 0.0);
+          for (size_t q = 0; q < Kt->keff_h.size(); ++q) pre[q + 1] = pre[q] + Kt->keff_h[q];
+          for (size_t sg = 0; sg < seg_i.size(); ++sg) {
+            const long long len = seg_off[sg + 1] - seg_off[sg];
+            prim_exec += (double)B->keff_h[seg_i[sg]] * (pre[seg_j0[sg] + len] - pre[seg_j0[sg]]);
+          }
+        }
         PlanItem it;
+        it.prim_exec = prim_exec;
         it.kb = kb; it.kk = kk; it.same = same; it.total = total;
         it.begin = total * rank / nranks;
         it.count = total * (rank + 1) / nranks - it.begin;
@@ -919,7 +949,7 @@ int pc_set_profiling(pc_basis* h, int on) {
 }
 
 int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim,
-                  long long* tasks, float* ms) {
+                  long long* tasks, float* ms, double* prim_exec) {
   if (!h || !n_items) return fail("pc_plan_items: null");
   if (!h->planned) return fail("pc_plan_items: call pc_plan first");
   *n_items = (int)h->plan.size();
@@ -931,6 +961,7 @@ int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim
     if (kprim) { kprim[2 * k] = B->K; kprim[2 * k + 1] = Kt->K; }
     if (tasks) { tasks[2 * k] = it.total; tasks[2 * k + 1] = it.count; }
     if (ms) ms[k] = k < (int)h->prof_ms.size() ? h->prof_ms[k] : 0.f;
+    if (prim_exec) prim_exec[k] = it.prim_exec;
   }
   return 0;
 }

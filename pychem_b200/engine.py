@@ -122,16 +122,19 @@ class DeviceBasis:
         """Per (bra bucket, ket bucket) launch: class, contraction depths, task counts and the
         device time of the last profiled accumulate."""
         n = ctypes.c_int()
-        _lib.check(self.lib.pc_plan_items(self.h, 0, ctypes.byref(n), None, None, None, None))
+        _lib.check(self.lib.pc_plan_items(self.h, 0, ctypes.byref(n), None, None, None, None, None))
         m = n.value
         cls = np.zeros((m, 4), dtype=np.int32)
         kprim = np.zeros((m, 2), dtype=np.int32)
         tasks = np.zeros((m, 2), dtype=np.int64)
         ms = np.zeros(m, dtype=np.float32)
+        prim = np.zeros(m, dtype=np.float64)
         _lib.check(self.lib.pc_plan_items(self.h, m, ctypes.byref(n), cls.ctypes.data_as(_lib.c_ip),
                                           kprim.ctypes.data_as(_lib.c_ip),
                                           tasks.ctypes.data_as(_lib.c_llp),
-                                          ms.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+                                          ms.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                          prim.ctypes.data_as(_lib.c_dp)))
+        self.prim_exec = prim
         return cls, kprim, tasks, ms
 
     # ------------------------------------------------------------------ ERIs
