@@ -133,6 +133,23 @@ int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim
 /* Kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int pc_launch_count(const pc_basis* h, long long* n);
 
+/*
+ * MP2: AO->MO four-index transform on the FP64 tensor cores (DMMA, mma.sync m8n8k4 f64) and the
+ * UMP2 energy sums.  Replaces the O(N^6) Python loops of Methods/mp2.py:37-94 (half transforms
+ * :43-69, energy sums :77-94).  G_dev: the dense tensor from pc_eri_tensor (device, N^4 doubles);
+ * Ca/Cb: MO coefficients (N x N, row-major, AO index first, as this_state.Alpha.MOs);
+ * Ea/Eb: orbital energies; na/nb: molecule.NAlphaElectrons / NBetaElectrons (mp2.py:78-91);
+ * same_spin = 0 skips the alpha-alpha and beta-beta sums ("P2-SOS", mp2.py:77).  Host or device
+ * pointers for C and E.  Outputs: the three unscaled sums MP2_Eaa, MP2_Eab, MP2_Ebb.
+ * Errors of these two-letter entry points are reported through pc_mp2_last_error().
+ */
+int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, const double* Cb,
+                  const double* Ea, const double* Eb, int na, int nb, int same_spin, double* Eaa,
+                  double* Eab, double* Ebb);
+const char* pc_mp2_last_error(void);
+/* C (M x N) = A (M x K) . B (K x N), row-major device buffers, through the same DMMA kernel. */
+int pc_dgemm_dmma(int device, int M, int N, int K, const double* A, const double* B, double* C);
+
 /* Register-resident DFMA micro-benchmark: measured FP64 FMA peak of `device` in TFLOP/s
  * (the roofline denominator for the ERI kernels; MEASURED_PEAKS.json has no FP64 entry). */
 int pc_fp64_peak(int device, double* tflops);

@@ -172,6 +172,19 @@ def main():
                         na=mol.NAlphaElectrons, nb=mol.NBetaElectrons)
     print("H3", repr(ehf), repr(emp2))
 
+    # ---------------- H2O 6-31G** RHF + MP2 (reference mp2.do, O(N^6) Python) -----------
+    inp = os.path.join(GOLD, "_h2o_mp2.inp")
+    ref_driver.write_input(inp, "h2omp2", S.H2O_MONOMER, "6-31G**", method="MP2")
+    t = time.time()
+    mol = ref_driver.run(inp)
+    os.remove(inp)
+    st = mol.States[0]
+    emp2 = [float(l.split()[-1]) for l in mol.OutText.splitlines() if "Total MP2 energy" in l][0]
+    np.savez_compressed(os.path.join(GOLD, "h2o_631gss_mp2.npz"), hf=st.TotalEnergy, mp2_total=emp2,
+                        Ca=st.Alpha.MOs, Cb=st.Beta.MOs, Ea=st.Alpha.Energies, Eb=st.Beta.Energies,
+                        na=mol.NAlphaElectrons, nb=mol.NBetaElectrons)
+    print("H2O MP2", repr(st.TotalEnergy), repr(emp2), "%.1fs" % (time.time() - t))
+
 
 if __name__ == "__main__":
     main()

@@ -35,6 +35,10 @@ SIGNATURES = {
     "pc_set_profiling": [c_vp, ctypes.c_int],
     "pc_plan_items": [c_vp, ctypes.c_int, c_ip, c_ip, c_ip, c_llp, ctypes.POINTER(ctypes.c_float), c_dp],
     "pc_fp64_peak": [ctypes.c_int, c_dp],
+    "pc_mp2_energy": [ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
+                      ctypes.c_int, c_dp, c_dp, c_dp],
+    "pc_mp2_last_error": [],
+    "pc_dgemm_dmma": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp],
 }
 
 _LIB = None
@@ -56,11 +60,13 @@ def load():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError if the ABI lost a symbol
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "pc_last_error" else ctypes.c_int
+            fn.restype = ctypes.c_char_p if name.endswith("last_error") else ctypes.c_int
         _LIB = lib
     return _LIB
 
 
-def check(status):
+def check(status, mp2=False):
     if status != 0:
-        raise PychemB200Error(load().pc_last_error().decode() or "pychem_b200: unknown error")
+        lib = load()
+        msg = (lib.pc_mp2_last_error() if mp2 else lib.pc_last_error()).decode()
+        raise PychemB200Error(msg or "pychem_b200: unknown error")

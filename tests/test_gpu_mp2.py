@@ -1,0 +1,130 @@
+"""GPU tests of the MP2 AO->MO transform on the FP64 tensor cores (csrc/pc_mp2.cu) behind the
+reference's mp2.do surface.  Goldens: reference's own mp2.do (oracle/make_golden.py).
+Bar: total MP2 energies within 1e-8 Eh (north_star)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_driver
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+E_TOL = 1.0e-8
+
+
+def test_dgemm_dmma_matches_numpy():
+    import torch
+    from pychem_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for M, N, K in ((64, 64, 16), (5, 7, 3), (130, 257, 96), (21, 884736 // 64, 96)):
+        A = torch.from_numpy(rng.uniform(-1, 1, (M, K))).cuda()
+        B = torch.from_numpy(rng.uniform(-1, 1, (K, N))).cuda()
+        C = torch.empty((M, N), dtype=torch.float64, device="cuda")
+        _lib.check(lib.pc_dgemm_dmma(0, M, N, K, ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()),
+                                     ctypes.c_void_p(C.data_ptr())), mp2=True)
+        ref = A.cpu().numpy() @ B.cpu().numpy()
+        assert np.abs(C.cpu().numpy() - ref).max() < 1e-12 * K
+
+
+class _M:
+    pass
+
+
+def _state(g):
+    st = _M()
+    st.Alpha, st.Beta = _M(), _M()
+    st.Alpha.MOs, st.Beta.MOs = g["Ca"], g["Cb"]
+    st.Alpha.Energies, st.Beta.Energies = g["Ea"], g["Eb"]
+    st.TotalEnergy = float(g["hf"])
+    return st
+
+
+def test_h2o_mp2_sums_vs_reference(gold):
+    """Restricted H2O/6-31G**: same MOs and orbital energies as the reference run, integrals from
+    the CUDA path; HF + MP2 total against the reference's mp2.do output."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
+    g = gold("h2o_631gss_mp2.npz")
+    mol = helpers.molecule("h2o")
+    mol.NAlphaElectrons, mol.NBetaElectrons = int(g["na"]), int(g["nb"])
+    hf_gpu.evaluate_2e_ints(mol)
+    st = _state(g)
+    Eaa, Eab, Ebb = mp2_gpu.mp2_sums(mol, st)
+    assert abs(st.TotalEnergy + Eaa + Eab + Ebb - float(g["mp2_total"])) < E_TOL
+    assert abs(Eaa - Ebb) < 1e-12                   # restricted orbitals
+    Eaa0, Eab0, Ebb0 = mp2_gpu.mp2_sums(mol, st, same_spin=False)
+    assert Eaa0 == 0.0 and Ebb0 == 0.0 and abs(Eab0 - Eab) < 1e-13
+    hf_gpu.release()
+    ints_gpu.release()
+
+
+def test_h3_open_shell_mp2_sums(gold):
+    """Tests/example1.inp (H3, STO-3G, CUHF, doublet): unrestricted sums with na != nb."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
+    g = gold("h3_sto3g_mp2.npz")
+    mol = helpers.molecule("h3")
+    assert (mol.NAlphaElectrons, mol.NBetaElectrons) == (int(g["na"]), int(g["nb"]))
+    hf_gpu.evaluate_2e_ints(mol)
+    st = _state(g)
+    Eaa, Eab, Ebb = mp2_gpu.mp2_sums(mol, st)
+    assert abs(st.TotalEnergy + Eaa + Eab + Ebb - float(g["mp2_total"])) < E_TOL
+    hf_gpu.release()
+    ints_gpu.release()
+
+
+@pytest.mark.skipif(not ref_driver.available(), reason="oracle/_ref (reference copy) not shipped")
+def test_dropin_mp2_through_reference_driver(gold):
+    """pychem.main on Tests/example1.inp with evaluate_2e_ints, make_coulomb_exchange_matrices AND
+    mp2.do rebound to the CUDA path: the line the reference writes to <section>.out must match."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
+    ns = ref_driver.modules()
+    undo1 = hf_gpu.install(ns.hartree_fock)
+    undo2 = mp2_gpu.install(ns.mp2)
+    try:
+        mol = ref_driver.run(os.path.join(ref_driver.REF_ROOT, "Tests", "example1.inp"))
+    finally:
+        undo1()
+        undo2()
+    g = gold("h3_sto3g_mp2.npz")
+    emp2 = [float(l.split()[-1]) for l in mol.OutText.splitlines() if "Total MP2 energy" in l][0]
+    assert abs(emp2 - float(g["mp2_total"])) < E_TOL
+    hf_gpu.release()
+    ints_gpu.release()
+
+
+def test_benzene_mp2_transform_vs_numpy():
+    """Benzene 6-31G* (N = 96, the BASELINE MP2 config): the DMMA transform + energy sums against
+    an O(N^5) numpy evaluation of the same formulas on the same (GPU-built) tensor, with
+    synthetic orthonormal orbitals."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
+    mol = helpers.molecule("benzene")
+    hf_gpu.evaluate_2e_ints(mol)
+    G = mol.CoulombIntegrals
+    N = mol.NOrbitals
+    rng = np.random.default_rng(5)
+    C, _ = np.linalg.qr(rng.uniform(-1, 1, (N, N)))
+    E = np.sort(rng.uniform(-2, 2, N))
+    E[mol.NAlphaElectrons:] += 3.0                 # keep the denominators away from zero
+    st = _M()
+    st.Alpha, st.Beta = _M(), _M()
+    st.Alpha.MOs = st.Beta.MOs = C
+    st.Alpha.Energies = st.Beta.Energies = E
+    Eaa, Eab, Ebb = mp2_gpu.mp2_sums(mol, st)
+    no = mol.NAlphaElectrons
+    Co, Cv = C[:, :no], C[:, no:]
+    T = np.einsum("mi,mnls->inls", Co, G, optimize=True)
+    T = np.einsum("np,inls->ipls", Cv, T, optimize=True)
+    T = np.einsum("lj,ipls->ipjs", Co, T, optimize=True)
+    T = np.einsum("sq,ipjs->ipjq", Cv, T, optimize=True)
+    D = E[:no, None, None, None] - E[None, no:, None, None] + E[None, None, :no, None] - E[None, None, None, no:]
+    Eab_ref = float(np.sum(T ** 2 / D))
+    A = T - T.transpose(0, 3, 2, 1)
+    i, p, j, q = np.ogrid[:no, :N - no, :no, :N - no]
+    Eaa_ref = float(np.sum(np.where((j <= i) & (q <= p), A ** 2 / D, 0.0)))
+    assert abs(Eab - Eab_ref) < 1e-10 * max(1.0, abs(Eab_ref))
+    assert abs(Eaa - Eaa_ref) < 1e-10 * max(1.0, abs(Eaa_ref))
+    assert abs(Ebb - Eaa) < 1e-12 * max(1.0, abs(Eaa))
+    hf_gpu.release()
+    ints_gpu.release()
