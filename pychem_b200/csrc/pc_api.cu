@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <numeric>
@@ -175,58 +176,92 @@ __global__ void jk_finalize_kernel(int N, int general, int nspin, const double* 
   }
 }
 
-// One CTA per (a,b) slab G[a,b,:,:] (N x N contiguous): streams the tensor exactly once.
+// One CTA per group of NB consecutive slabs G[a,b..b+NB-1,:,:] (each N x N contiguous): streams
+// the tensor exactly once and re-uses every Dt[c,d] load for NB slabs.
 //   J[a,b]   = sum_cd Dt[c,d] G[a,b,c,d]
 //   Xa[a,d] -= sum_c  Da[c,b] G[a,b,c,d]   (and beta)
-__global__ void __launch_bounds__(256) jk_stored_kernel(int N, const double* __restrict__ G,
+// 8 warps; a warp covers 32*VEC consecutive columns d of one row c per load (16-byte loads when
+// N is even), the 8 warps take rows c, c+8, ...
+template <int VEC, int NB>
+__global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const double* __restrict__ G,
                                                         const double* __restrict__ Dt,
                                                         const double* __restrict__ Da,
                                                         const double* __restrict__ Db,
                                                         double* __restrict__ J,
                                                         double* __restrict__ Xa,
                                                         double* __restrict__ Xb) {
-  const int a = blockIdx.x / N, b = blockIdx.x % N;
-  const double* __restrict__ slab = G + (size_t)blockIdx.x * N * N;
-  // threads: x over d (coalesced), y over c-chunks
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32, ny = blockDim.x / 32;
-  double jsum = 0.0;
-  __shared__ double red[8][33];
-  for (int d0 = 0; d0 < N; d0 += 32) {
-    const int d = d0 + tx;
-    double xa = 0.0, xb = 0.0;
+  const int a = blockIdx.x / ngrp, b0 = (blockIdx.x % ngrp) * NB;
+  const int nbv = min(NB, N - b0);                      // slabs of this group that exist
+  const size_t NN = (size_t)N * N;
+  const double* __restrict__ slab = G + ((size_t)a * N + b0) * NN;
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  constexpr int RG = 8;
+  __shared__ double red[2][RG][32 * VEC + 1];
+  double jsum[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) jsum[k] = 0.0;
+  for (int d0 = 0; d0 < N; d0 += 32 * VEC) {
+    const int d = d0 + lane * VEC;
+    double xa[VEC], xb[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) xa[v] = xb[v] = 0.0;
     if (d < N) {
-      for (int c = ty; c < N; c += ny) {
-        const double g = slab[(size_t)c * N + d];
-        jsum = fma(Dt[(size_t)c * N + d], g, jsum);
-        xa = fma(Da[(size_t)c * N + b], g, xa);
-        xb = fma(Db[(size_t)c * N + b], g, xb);
+#pragma unroll 2
+      for (int c = rg; c < N; c += RG) {
+        double t[VEC];
+        if (VEC == 2) {
+          const double2 t2 = __ldg(reinterpret_cast<const double2*>(Dt + (size_t)c * N + d));
+          t[0] = t2.x; t[VEC - 1] = t2.y;
+        } else {
+          t[0] = __ldg(Dt + (size_t)c * N + d);
+        }
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          if (k < nbv) {
+            const double da = __ldg(Da + (size_t)c * N + b0 + k), db = __ldg(Db + (size_t)c * N + b0 + k);
+            double g[VEC];
+            if (VEC == 2) {
+              const double2 g2 = *reinterpret_cast<const double2*>(slab + (size_t)k * NN + (size_t)c * N + d);
+              g[0] = g2.x; g[VEC - 1] = g2.y;
+            } else {
+              g[0] = slab[(size_t)k * NN + (size_t)c * N + d];
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              jsum[k] = fma(t[v], g[v], jsum[k]);
+              xa[v] = fma(da, g[v], xa[v]);
+              xb[v] = fma(db, g[v], xb[v]);
+            }
+          }
+        }
       }
     }
-    red[ty][tx] = xa;
-    __syncthreads();
-    if (ty == 0 && d < N) {
-      double s = 0.0;
-      for (int k = 0; k < ny; ++k) s += red[k][tx];
-      atomicAdd(&Xa[(size_t)a * N + d], -s);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      red[0][rg][lane * VEC + v] = xa[v];
+      red[1][rg][lane * VEC + v] = xb[v];
     }
     __syncthreads();
-    red[ty][tx] = xb;
-    __syncthreads();
-    if (ty == 0 && d < N) {
-      double s = 0.0;
-      for (int k = 0; k < ny; ++k) s += red[k][tx];
-      atomicAdd(&Xb[(size_t)a * N + d], -s);
+    const int col = threadIdx.x % (32 * VEC), which = threadIdx.x / (32 * VEC);
+    if (which < 2 && d0 + col < N) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < RG; ++k) sum += red[which][k][col];
+      atomicAdd((which ? Xb : Xa) + (size_t)a * N + d0 + col, -sum);
     }
     __syncthreads();
   }
-  // block reduction of jsum
-  for (int o = 16; o > 0; o >>= 1) jsum += __shfl_xor_sync(0xffffffffu, jsum, o);
-  if (tx == 0) red[ty][0] = jsum;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    double v = jsum[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[0][rg][k] = v;
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int k = 0; k < ny; ++k) s += red[k][0];
-    J[(size_t)a * N + b] = s;
+  if (threadIdx.x < nbv) {
+    double sum = 0.0;
+    for (int k = 0; k < RG; ++k) sum += red[0][k][threadIdx.x];
+    J[(size_t)a * N + b0 + threadIdx.x] = sum;
   }
 }
 
@@ -844,7 +879,12 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
       stage_in(h, Db, h->dstage.p + 2 * nn, &db)) return 1;
   double* o = h->ostage.p;
   PC_CUDA(cudaMemsetAsync(o, 0, 3 * nn * sizeof(double), h->stream));
-  jk_stored_kernel<<<N * N, 256, 0, h->stream>>>(N, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+  {
+    constexpr int NBG = 4;                       // slabs per CTA
+    const int ngrp = (N + NBG - 1) / NBG;
+    if (N % 2 == 0) jk_stored_kernel<2, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+    else jk_stored_kernel<1, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+  }
   PC_CUDA(cudaGetLastError());
   h->launches += 1;
   if (copy_out(h, o, J) || copy_out(h, o + nn, Xa) || copy_out(h, o + 2 * nn, Xb)) return 1;
@@ -884,7 +924,11 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
       h->prof_events.push_back(e);
     }
   }
-  const int NSIDE = 8;
+  static const int NSIDE = []() {
+    const char* e = getenv("PYCHEM_B200_STREAMS");     // tuning knob (default 8 side streams)
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : (v > 64 ? 64 : v);
+  }();
   const bool fan = !h->profiling && h->plan.size() > 1;
   if (fan) {
     while ((int)h->side.size() < NSIDE) {
