@@ -294,7 +294,7 @@ class ClassGen:
         override = os.environ.get("PC_GEN_MINB_L%d" % self.L)
         if override:
             return int(override)
-        return {0: 8, 1: 8}.get(self.L, 1)
+        return {0: 8, 1: 8, 2: 6, 3: 4}.get(self.L, 1)   # tuned on (H2O)32, profiles/README.md
 
     def source(self):
         lx1, ly1, lx2, ly2 = self.l
