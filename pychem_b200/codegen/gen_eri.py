@@ -615,7 +615,7 @@ class ClassGenV2(ClassGen):
         return lines
 
 
-V2_THRESHOLD = 600      # classes with more VRR temporaries than this use the rolled form
+V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
 
 
 def make_class(cls):
