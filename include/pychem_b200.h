@@ -62,9 +62,10 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax);
  * Build the screened, class-bucketed shell-quartet schedule.
  *   Replaces the loop nest + screen of pass 2 (Methods/hartree_fock.py:276-295): a unique
  *   quartet (ab|cd) survives iff max(B_ab)*max(B_cd) > thresh (strict), diagonal quartets
- *   (ab|ab) always do.  Within every (bra bucket, ket bucket) the task range is cut into
- *   nranks equal contiguous slices (cost is uniform inside a bucket pair) and this handle keeps
- *   slice `rank` -- the static cost-balanced multi-GPU partition.
+ *   (ab|ab) always do.  Static cost-balanced multi-GPU partition: the task range of every large
+ *   (bra bucket, ket bucket) is cut into nranks equal contiguous slices (cost is uniform inside a
+ *   bucket pair) and this handle keeps slice `rank`; the cheapest bucket pairs (together <= 15 %
+ *   of the flop-model cost) are handed out whole, longest first, to the least loaded rank.
  *   Outputs (may be NULL): quartets/eris kept by this rank, and in total.
  */
 int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quartets,

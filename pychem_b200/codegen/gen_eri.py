@@ -677,6 +677,14 @@ def main(outdir):
             row.append("pc_launch_%s" % "".join(LNAME[x] for x in b + k) if ik <= ib else "nullptr")
         tab.append("  {" + ", ".join(row) + "},")
     tab.append("};")
+    for key, label in (("flop_prim", "pc_flop_prim_table"), ("flop_cont", "pc_flop_cont_table")):
+        tab.append("double %s[6][6] = {" % label)
+        for ib, b in enumerate(PAIR_CLASSES):
+            row = []
+            for ik, k in enumerate(PAIR_CLASSES):
+                row.append(str(float(model["".join(LNAME[x] for x in b + k)][key])) if ik <= ib else "0.0")
+            tab.append("  {" + ", ".join(row) + "},")
+        tab.append("};")
     tab.append("int pc_block_table[6][6] = {")
     for ib, b in enumerate(PAIR_CLASSES):
         row = []

@@ -654,6 +654,7 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     h->plan.clear();
     std::vector<long long> seg_off;
     std::vector<int> seg_i, seg_j0;
+    std::vector<std::vector<long long>> host_seg_off;
     h->my_quartets = h->my_eris = h->all_quartets = h->all_eris = 0;
     const int nk = (int)h->kinds.size();
     for (int ka = 0; ka < nk; ++ka)
@@ -713,8 +714,8 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         PlanItem it;
         it.prim_exec = prim_exec;
         it.kb = kb; it.kk = kk; it.same = same; it.total = total;
-        it.begin = total * rank / nranks;
-        it.count = total * (rank + 1) / nranks - it.begin;
+        it.begin = 0;
+        it.count = total;
         it.nseg = (int)seg_i.size();
         it.seg_off = new DevBuf<long long>();
         h->plan_bufs.push_back(it.seg_off);
@@ -726,31 +727,72 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         std::vector<int> ij(2 * seg_i.size());
         for (size_t k = 0; k < seg_i.size(); ++k) { ij[2 * k] = seg_i[k]; ij[2 * k + 1] = seg_j0[k]; }
         PC_CUDA(it.seg_ij->upload(ij, h->stream));
-        std::vector<int> s0;
-        {
-          // segment of every warp's first task
-          const long long nwarp = (it.count + 31) / 32;
-          s0.resize((size_t)nwarp);
-          int cur = 0;
-          for (long long w = 0; w < nwarp; ++w) {
-            const long long g0 = it.begin + w * 32;
-            while (seg_off[cur + 1] <= g0) ++cur;
-            s0[(size_t)w] = cur;
-          }
-          PC_CUDA(it.warp_s0->upload(s0, h->stream));
-        }
         PC_CUDA(cudaStreamSynchronize(h->stream));
-        const long long nsph = (long long)(2 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
-        h->all_quartets += total; h->all_eris += total * nsph;
-        h->my_quartets += it.count; h->my_eris += it.count * nsph;
+        host_seg_off.push_back(seg_off);
         h->plan.push_back(it);
       }
-    // longest-first launch order (rough cost ~ quartets * primitive quartets * (L+1)^3)
-    auto cost = [&](const PlanItem& it) {
+    // ---- static multi-GPU schedule: cost model = flop model of the class.
+    // Large bucket pairs are cut into nranks equal contiguous slices (cost inside a bucket pair
+    // is uniform -> exactly balanced).  The many small bucket pairs (the cheapest ones, together
+    // <= 15 % of the modelled cost) are NOT sliced -- a slice of a small launch does not fill a
+    // GPU -- but handed out whole, longest first, to the least loaded rank (LPT).
+    auto cost_total = [&](const PlanItem& it) {
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
-      const double L1 = B->lx + B->ly + Kt->lx + Kt->ly + 1;
-      return (double)it.count * ((double)B->K * Kt->K + 4.0) * L1 * L1 * L1;
+      const double nsph = (2.0 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
+      return it.prim_exec * pc_flop_prim_table[B->pc][Kt->pc] +
+             (double)it.total * (pc_flop_cont_table[B->pc][Kt->pc] + 40.0 * nsph + 60.0);
+    };
+    {
+      std::vector<int> order(h->plan.size());
+      std::iota(order.begin(), order.end(), 0);
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return cost_total(h->plan[a]) > cost_total(h->plan[b]);
+      });
+      double all = 0;
+      for (const PlanItem& it : h->plan) all += cost_total(it);
+      std::vector<double> load(nranks, 0.0);
+      double cum = 0;
+      for (int idx : order) {
+        PlanItem& it = h->plan[idx];
+        const double c = cost_total(it);
+        cum += c;
+        const bool whole = nranks > 1 && cum > 0.85 * all;
+        if (!whole) {
+          it.begin = it.total * rank / nranks;
+          it.count = it.total * (rank + 1) / nranks - it.begin;
+        } else {
+          const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+          load[r] += c;
+          it.begin = 0;
+          it.count = (r == rank) ? it.total : 0;
+        }
+      }
+    }
+    for (size_t k = 0; k < h->plan.size(); ++k) {
+      PlanItem& it = h->plan[k];
+      const Kind* B = h->kinds[it.kb];
+      const Kind* Kt = h->kinds[it.kk];
+      const std::vector<long long>& so = host_seg_off[k];
+      // segment of every warp's first task
+      const long long nwarp = (it.count + 31) / 32;
+      std::vector<int> s0((size_t)nwarp);
+      int cur = 0;
+      for (long long w = 0; w < nwarp; ++w) {
+        const long long g0 = it.begin + w * 32;
+        while (so[cur + 1] <= g0) ++cur;
+        s0[(size_t)w] = cur;
+      }
+      PC_CUDA(it.warp_s0->upload(s0, h->stream));
+      PC_CUDA(cudaStreamSynchronize(h->stream));
+      const long long nsph = (long long)(2 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
+      h->all_quartets += it.total; h->all_eris += it.total * nsph;
+      h->my_quartets += it.count; h->my_eris += it.count * nsph;
+    }
+    host_seg_off.clear();
+    // longest-first launch order
+    auto cost = [&](const PlanItem& it) {
+      return it.total ? cost_total(it) * ((double)it.count / (double)it.total) : 0.0;
     };
     std::stable_sort(h->plan.begin(), h->plan.end(),
                      [&](const PlanItem& a, const PlanItem& b) { return cost(a) > cost(b); });
