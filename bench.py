@@ -385,38 +385,31 @@ def run_b200(args):
     top = max(per_class.items(), key=lambda kv: kv[1]["ms"])
     eri_ms = sum(v["ms"] for v in per_class.values())
     achieved = all_flops / (ms_step * 1e-3) / 1e12 / world      # per-GPU TFLOP/s over the whole step
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
+    # dominant kernel = the class kernel with the largest share of the step (per-launch CUDA-event
+    # times of one profiled build).  `traffic`: DRAM bytes of its largest launch from the committed
+    # ncu --set full capture (profiles/r1_final_ncu_full_eri_psss_jk.txt) -- everything is
+    # L2-resident, the path is not HBM-bound.
+    top_tf = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 if top[1]["ms"] else None
+    roofline = {"bound": "fp64", "achieved": top_tf, "peak": peak, "unit": "TFLOP/s",
+                "frac": (top_tf / peak) if (top_tf and peak) else None,
+                "traffic": 19.4e6 if top[0] == "psss" else None,
+                "kernel": "eri_%s_kernel<JK_RHF>: %d launches per build (one per bucket pair), %.3f ms "
+                          "serialised, %.1f%% of the serialised per-class total"
+                          % (top[0], sum(1 for c in db.plan_items()[0] if "spd"[c[0]] + "spd"[c[1]] + "spd"[c[2]] + "spd"[c[3]] == top[0]),
+                             top[1]["ms"], 100.0 * top[1]["ms"] / eri_ms if eri_ms else 0.0),
                 "peak_source": "pc_fp64_peak: register-resident DFMA loop measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
-                "kernel": "all eri_*_kernel<JK_RHF> launches of one Fock build (%d per step)" % launches,
-                "eri_kernels_share_of_step": eri_ms / ms_step if ms_step else None,
-                "dominant_kernel": {"name": "eri_%s_kernel" % top[0], "ms": top[1]["ms"],
-                                    "share_of_step": top[1]["ms"] / ms_step,
-                                    "achieved": top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 if top[1]["ms"] else None,
-                                    "frac": (top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 / peak) if top[1]["ms"] and peak else None},
-                "algorithmic_gflop_per_step": all_flops / 1e9,
-                "reference_unscreened_gflop_per_step": ref_flops / 1e9,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the longest launch, ncu --set full, "
+                                  "profiles/r1_final_ncu_full_eri_psss_jk.txt",
+                "whole_step": {"achieved": achieved, "frac": achieved / peak if peak else None,
+                               "kernels": "all %d eri_*_kernel<JK_RHF> launches of one Fock build, concurrent on 8 "
+                                          "streams, replayed as one CUDA graph" % launches,
+                               "algorithmic_gflop_per_step": all_flops / 1e9,
+                               "reference_unscreened_gflop_per_step": ref_flops / 1e9,
+                               "serialised_kernel_ms_over_step_ms": eri_ms / ms_step if ms_step else None},
                 "flop_count": "executed primitive quartets (after the 1e-24 primitive-pair cut-off) * flop_prim "
-                              "+ quartets * (flop_cont + digestion); the reference's unscreened primitive "
-                              "loops would be reference_unscreened_gflop_per_step"}
-    # pure ERI generation (same schedule, integrals discarded): the "FP64 ERIs/sec" of generation
-    def step_eri_only():
-        _lib.check(lib.pc_jk_direct_accumulate(db.h, 5, P(Dt_d), P(Da_d), P(Da_d), P(acc)))
-    step_eri_only()
-    eri_only_ms = timed(step_eri_only, max(args.steps, 2)) / max(args.steps, 2)
-    if args.profile_classes and rank == 0:
-        db.set_profiling(True)
-        step_eri_only()
-        db.set_profiling(False)
-        cls2, kprim2, tasks2, ms2 = db.plan_items()
-        gen = {}
-        for (l1, l2, l3, l4), t in zip(cls2, ms2):
-            nm = "spd"[l1] + "spd"[l2] + "spd"[l3] + "spd"[l4]
-            gen[nm] = gen.get(nm, 0.0) + float(t)
-        cls_, kprim_, tasks_, ms_ = cls2, kprim2, tasks2, None
-        for k, v in sorted(per_class.items(), key=lambda kv: -kv[1]["ms"]):
-            v["gen_ms"] = gen.get(k, 0.0)
+                              "+ quartets * (flop_cont + digestion), SURVEY 8(d) model on the generator's DAG "
+                              "(pychem_b200/data/flop_model.json)"}
     if args.profile_classes and rank == 0:
         for k, v in sorted(per_class.items(), key=lambda kv: -kv[1]["ms"]):
             tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else 0.0
