@@ -355,16 +355,22 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = counts["all_eris"] / (ms_step * 1e-3)
 
-    if rank == 0 and clocks.get("samples", 0) == 0:
-        # still nothing (very few steps): keep the same load running for 0.5 s and sample that
-        sampler = ClockSampler(local)
-        sampler.start()
-        t_end = time.perf_counter() + 0.5
-        while time.perf_counter() < t_end:
+    if ms_total < 400.0:
+        # timed region shorter than a few nvidia-smi periods: keep the same load running for
+        # ~0.5 s (same iteration count on every rank) and sample the clocks under it
+        n_extra = int(500.0 / max(ms_step, 1e-3)) + 1
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
+        for _ in range(n_extra):
             step_device()
-        torch.cuda.synchronize()
-        clocks = sampler.stop()
-        clocks["note"] = "timed region shorter than one nvidia-smi period; sampled over 0.5 s of the same steps right after it"
+        barrier()
+        if rank == 0:
+            extra = sampler2.stop()
+            if extra.get("samples", 0) > clocks.get("samples", 0):
+                clocks = extra
+                clocks["note"] = ("timed region of %.0f ms is shorter than a few nvidia-smi periods; sampled over "
+                                  "%d more identical steps right after it" % (ms_total, n_extra))
     # ---- e2e through the plugin call with host buffers --------------------------------------
     hf_gpu._STATE[id(mol)] = {"mode": "direct", "db": db, "G_dev": None, "molecule": mol}
     Dt_p = torch.from_numpy(Dt_h).pin_memory()
