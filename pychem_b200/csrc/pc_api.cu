@@ -7,6 +7,9 @@
 #include "pc_common.cuh"
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -652,90 +655,94 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     for (auto* b : h->plan_ibufs) delete b;
     h->plan_ibufs.clear();
     h->plan.clear();
-    std::vector<long long> seg_off;
-    std::vector<int> seg_i, seg_j0;
-    std::vector<std::vector<long long>> host_seg_off;
     h->my_quartets = h->my_eris = h->all_quartets = h->all_eris = 0;
+    // ---- phase A (host threads): the segments of every (bra bucket, ket bucket) ------------
+    struct Work {
+      int kb, kk, same;
+      std::vector<long long> seg_off;
+      std::vector<int> ij, s0;
+      double prim_exec = 0;
+    };
+    std::vector<Work> work;
     const int nk = (int)h->kinds.size();
     for (int ka = 0; ka < nk; ++ka)
       for (int kb2 = ka; kb2 < nk; ++kb2) {
-        int kb = ka, kk = kb2;
-        if (h->kinds[kb]->pc < h->kinds[kk]->pc) std::swap(kb, kk);
-        const Kind* B = h->kinds[kb];
-        const Kind* Kt = h->kinds[kk];
-        const int same = (kb == kk);
-        const int nb = (int)B->pairs.size();
-        const int ng = (int)Kt->gstart.size() - 1;
-        // segments: (bra pair i) x (prefix of one ket group).  The test is the reference's:
-        // max(B_ab)*max(B_cd) > thresh, strict (hartree_fock.py:293-294); unique quartets only
-        // (ket position >= bra position inside one bucket); the diagonal (ab|ab) is always kept
-        // (hartree_fock.py:244-250).
-        seg_off.assign(1, 0);
-        seg_i.clear();
-        seg_j0.clear();
-        for (int i = 0; i < nb; ++i) {
-          const double pb = B->pm[i];
-          bool diag = !same;
-          for (int g = 0; g < ng; ++g) {
-            const int gs = Kt->gstart[g], ge = Kt->gstart[g + 1];
-            if (!(pb * Kt->pm[gs] > thresh)) break;       // groups are ordered by their maximum
-            int lo = gs, hi = ge;                          // first position that fails the test
-            while (hi - lo > 1) {
-              const int mid = (lo + hi) >> 1;
-              if (pb * Kt->pm[mid] > thresh) lo = mid; else hi = mid;
-            }
-            int j0 = gs;
-            const int j1 = hi;
-            if (same) j0 = std::max(j0, i);
-            if (j1 <= j0) continue;
-            if (same && i >= j0 && i < j1) diag = true;
-            seg_i.push_back(i);
-            seg_j0.push_back(j0);
-            seg_off.push_back(seg_off.back() + (j1 - j0));
-          }
-          if (!diag) {
-            seg_i.push_back(i);
-            seg_j0.push_back(i);
-            seg_off.push_back(seg_off.back() + 1);
-          }
-        }
-        const long long total = seg_off.back();
-        if (total == 0) continue;
-        // executed primitive quartets: sum over segments of keff(bra) * sum keff(kets)
-        double prim_exec = 0;
-        {
-          std::vector<double> pre(Kt->keff_h.size() + 1, 0.0);
-          for (size_t q = 0; q < Kt->keff_h.size(); ++q) pre[q + 1] = pre[q] + Kt->keff_h[q];
-          for (size_t sg = 0; sg < seg_i.size(); ++sg) {
-            const long long len = seg_off[sg + 1] - seg_off[sg];
-            prim_exec += (double)B->keff_h[seg_i[sg]] * (pre[seg_j0[sg] + len] - pre[seg_j0[sg]]);
-          }
-        }
-        PlanItem it;
-        it.prim_exec = prim_exec;
-        it.kb = kb; it.kk = kk; it.same = same; it.total = total;
-        it.begin = 0;
-        it.count = total;
-        it.nseg = (int)seg_i.size();
-        it.seg_off = new DevBuf<long long>();
-        h->plan_bufs.push_back(it.seg_off);
-        it.seg_ij = new DevBuf<int>();
-        it.warp_s0 = new DevBuf<int>();
-        h->plan_ibufs.push_back(it.seg_ij);
-        h->plan_ibufs.push_back(it.warp_s0);
-        PC_CUDA(it.seg_off->upload(seg_off, h->stream));
-        std::vector<int> ij(2 * seg_i.size());
-        for (size_t k = 0; k < seg_i.size(); ++k) { ij[2 * k] = seg_i[k]; ij[2 * k + 1] = seg_j0[k]; }
-        PC_CUDA(it.seg_ij->upload(ij, h->stream));
-        PC_CUDA(cudaStreamSynchronize(h->stream));
-        host_seg_off.push_back(seg_off);
-        h->plan.push_back(it);
+        Work w;
+        w.kb = ka; w.kk = kb2;
+        if (h->kinds[w.kb]->pc < h->kinds[w.kk]->pc) std::swap(w.kb, w.kk);
+        w.same = (w.kb == w.kk);
+        work.push_back(std::move(w));
       }
-    // ---- static multi-GPU schedule: cost model = flop model of the class.
-    // Large bucket pairs are cut into nranks equal contiguous slices (cost inside a bucket pair
-    // is uniform -> exactly balanced).  The many small bucket pairs (the cheapest ones, together
-    // <= 15 % of the modelled cost) are NOT sliced -- a slice of a small launch does not fill a
-    // GPU -- but handed out whole, longest first, to the least loaded rank (LPT).
+    auto build_segments = [&](Work& w) {
+      const Kind* B = h->kinds[w.kb];
+      const Kind* Kt = h->kinds[w.kk];
+      const int nb = (int)B->pairs.size();
+      const int ng = (int)Kt->gstart.size() - 1;
+      // segments: (bra pair i) x (prefix of one ket group).  The test is the reference's:
+      // max(B_ab)*max(B_cd) > thresh, strict (hartree_fock.py:293-294); unique quartets only
+      // (ket position >= bra position inside one bucket); the diagonal (ab|ab) is always kept
+      // (hartree_fock.py:244-250).
+      std::vector<double> pre(Kt->keff_h.size() + 1, 0.0);
+      for (size_t q = 0; q < Kt->keff_h.size(); ++q) pre[q + 1] = pre[q] + Kt->keff_h[q];
+      w.seg_off.assign(1, 0);
+      auto emit = [&](int i, int j0, int len) {
+        w.ij.push_back(i);
+        w.ij.push_back(j0);
+        w.seg_off.push_back(w.seg_off.back() + len);
+        w.prim_exec += (double)B->keff_h[i] * (pre[j0 + len] - pre[j0]);
+      };
+      for (int i = 0; i < nb; ++i) {
+        const double pb = B->pm[i];
+        bool diag = !w.same;
+        for (int g = 0; g < ng; ++g) {
+          const int gs = Kt->gstart[g], ge = Kt->gstart[g + 1];
+          if (!(pb * Kt->pm[gs] > thresh)) break;       // groups are ordered by their maximum
+          int lo = gs, hi = ge;                          // first position that fails the test
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pb * Kt->pm[mid] > thresh) lo = mid; else hi = mid;
+          }
+          int j0 = gs;
+          const int j1 = hi;
+          if (w.same) j0 = std::max(j0, i);
+          if (j1 <= j0) continue;
+          if (w.same && i >= j0 && i < j1) diag = true;
+          emit(i, j0, j1 - j0);
+        }
+        if (!diag) emit(i, i, 1);
+      }
+    };
+    auto parallel_for = [&](size_t n, const std::function<void(size_t)>& fn) {
+      const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+      std::atomic<size_t> next(0);
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < hw; ++t)
+        pool.emplace_back([&]() {
+          for (size_t k = next.fetch_add(1); k < n; k = next.fetch_add(1)) fn(k);
+        });
+      for (auto& th : pool) th.join();
+    };
+    parallel_for(work.size(), [&](size_t k) { build_segments(work[k]); });
+    // ---- phase B: plan items + static multi-GPU schedule ---------------------
+    // cost model = flop model of the class.  Large bucket pairs are cut into nranks equal
+    // contiguous slices (cost inside a bucket pair is uniform -> exactly balanced).  The many
+    // small bucket pairs (the cheapest ones, together <= 15 % of the modelled cost) are NOT
+    // sliced -- a slice of a small launch does not fill a GPU -- but handed out whole, longest
+    // first, to the least loaded rank (LPT).
+    std::vector<int> widx;       // work index of every plan item
+    for (size_t k = 0; k < work.size(); ++k) {
+      Work& w = work[k];
+      if (w.seg_off.back() == 0) continue;
+      PlanItem it;
+      it.kb = w.kb; it.kk = w.kk; it.same = w.same;
+      it.total = w.seg_off.back();
+      it.begin = 0; it.count = it.total;
+      it.prim_exec = w.prim_exec;
+      it.nseg = (int)w.ij.size() / 2;
+      it.seg_off = nullptr; it.seg_ij = nullptr; it.warp_s0 = nullptr;
+      h->plan.push_back(it);
+      widx.push_back((int)k);
+    }
     auto cost_total = [&](const PlanItem& it) {
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
@@ -769,27 +776,41 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         }
       }
     }
+    // ---- phase C (host threads): segment of every warp's first task ------------------------
+    parallel_for(h->plan.size(), [&](size_t k) {
+      const PlanItem& it = h->plan[k];
+      Work& w = work[widx[k]];
+      const long long nwarp = (it.count + 31) / 32;
+      w.s0.resize((size_t)nwarp);
+      int cur = 0;
+      for (long long wi = 0; wi < nwarp; ++wi) {
+        const long long g0 = it.begin + wi * 32;
+        while (w.seg_off[cur + 1] <= g0) ++cur;
+        w.s0[(size_t)wi] = cur;
+      }
+    });
+    // ---- phase D: uploads (one synchronisation at the end) ---------------------------------
     for (size_t k = 0; k < h->plan.size(); ++k) {
       PlanItem& it = h->plan[k];
+      const Work& w = work[widx[k]];
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
-      const std::vector<long long>& so = host_seg_off[k];
-      // segment of every warp's first task
-      const long long nwarp = (it.count + 31) / 32;
-      std::vector<int> s0((size_t)nwarp);
-      int cur = 0;
-      for (long long w = 0; w < nwarp; ++w) {
-        const long long g0 = it.begin + w * 32;
-        while (so[cur + 1] <= g0) ++cur;
-        s0[(size_t)w] = cur;
+      it.seg_off = new DevBuf<long long>();
+      h->plan_bufs.push_back(it.seg_off);
+      it.seg_ij = new DevBuf<int>();
+      it.warp_s0 = new DevBuf<int>();
+      h->plan_ibufs.push_back(it.seg_ij);
+      h->plan_ibufs.push_back(it.warp_s0);
+      if (it.count > 0) {
+        PC_CUDA(it.seg_off->upload(w.seg_off, h->stream));
+        PC_CUDA(it.seg_ij->upload(w.ij, h->stream));
+        PC_CUDA(it.warp_s0->upload(w.s0, h->stream));
       }
-      PC_CUDA(it.warp_s0->upload(s0, h->stream));
-      PC_CUDA(cudaStreamSynchronize(h->stream));
       const long long nsph = (long long)(2 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
       h->all_quartets += it.total; h->all_eris += it.total * nsph;
       h->my_quartets += it.count; h->my_eris += it.count * nsph;
     }
-    host_seg_off.clear();
+    PC_CUDA(cudaStreamSynchronize(h->stream));      // host vectors in `work` die below
     // longest-first launch order
     auto cost = [&](const PlanItem& it) {
       return it.total ? cost_total(it) * ((double)it.count / (double)it.total) : 0.0;
