@@ -172,6 +172,20 @@ def main():
                         na=mol.NAlphaElectrons, nb=mol.NBetaElectrons)
     print("H3", repr(ehf), repr(emp2))
 
+    # ---------------- LiH chains, SFS-NOCI (Tests/LiH_SFS_NOCI.test.inp scaled up) --------
+    for k in (2, 3):
+        inp = os.path.join(GOLD, "_lih%d.inp" % k)
+        ref_driver.write_input(inp, "lih%d" % k, S.lih_chain(k), "6-31G", method="NOCI", reference="UHF",
+                               extra='Constrain_Excited = True\nExcitations = "SFS"')
+        t = time.time()
+        mol = ref_driver.run(inp)
+        os.remove(inp)
+        np.savez_compressed(os.path.join(GOLD, "lih_chain%d_noci.npz" % k),
+                            hf=np.array([s.TotalEnergy for s in mol.States]),
+                            noci=np.asarray(mol.NOCIEnergies), nbf=mol.NOrbitals)
+        print("LiH chain", k, mol.NOrbitals, [s.TotalEnergy for s in mol.States], mol.NOCIEnergies,
+              "%.1fs" % (time.time() - t))
+
     # ---------------- H2O 6-31G** RHF + MP2 (reference mp2.do, O(N^6) Python) -----------
     inp = os.path.join(GOLD, "_h2o_mp2.inp")
     ref_driver.write_input(inp, "h2omp2", S.H2O_MONOMER, "6-31G**", method="MP2")
