@@ -62,10 +62,10 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax);
  * Build the screened, class-bucketed shell-quartet schedule.
  *   Replaces the loop nest + screen of pass 2 (Methods/hartree_fock.py:276-295): a unique
  *   quartet (ab|cd) survives iff max(B_ab)*max(B_cd) > thresh (strict), diagonal quartets
- *   (ab|ab) always do.  Static cost-balanced multi-GPU partition: the task range of every large
+ *   (ab|ab) always do.  Static cost-balanced multi-GPU partition: the task range of every
  *   (bra bucket, ket bucket) is cut into nranks equal contiguous slices (cost is uniform inside a
- *   bucket pair) and this handle keeps slice `rank`; the cheapest bucket pairs (together <= 15 %
- *   of the flop-model cost) are handed out whole, longest first, to the least loaded rank.
+ *   bucket pair, so the schedule is exactly balanced) and this handle keeps slice `rank`; all
+ *   bucket pairs of one angular-momentum class run in ONE fused kernel launch.
  *   Outputs (may be NULL): quartets/eris kept by this rank, and in total.
  */
 int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quartets,
@@ -119,9 +119,9 @@ int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, c
 int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double* Db, int* variant);
 
 /*
- * Measurement hooks (bench.py): with profiling on, pc_jk_direct_accumulate brackets every plan
- * item (one kernel launch per (bra bucket, ket bucket)) with CUDA events on the launching stream
- * and synchronises at the end.  pc_plan_items reports, per item k: cls[4k..] = (lx1,ly1,lx2,ly2),
+ * Measurement hooks (bench.py): with profiling on, pc_jk_direct_accumulate brackets every kernel
+ * launch (one fused launch per angular-momentum class; its time is booked on the first bucket
+ * pair of the class) with CUDA events on the launching stream and synchronises at the end.  pc_plan_items reports, per item k: cls[4k..] = (lx1,ly1,lx2,ly2),
  * kprim[2k..] = primitive pairs per bra/ket shell pair, tasks[2k..] = (all quartets, this rank's
  * quartets), ms[k] = device time of the item in the last profiled accumulate, prim_exec[k] =
  * primitive quartets the whole bucket pair actually visits (after the primitive-pair cut-off;

@@ -258,8 +258,8 @@ class ClassGen:
     def prim_prologue(self, s, nmax):
         """Primitive loops: ket primitives outside (per-lane, coalesced loads, once per ket
         primitive), bra primitives inside (warp-uniform addresses -> broadcast loads)."""
-        s.append("  const double2* __restrict__ bp = reinterpret_cast<const double2*>(A.bra.prim) + i;")
-        s.append("  const double2* __restrict__ kp = reinterpret_cast<const double2*>(A.ket.prim) + j;")
+        s.append("  const double2* __restrict__ bp = reinterpret_cast<const double2*>(I.bra.prim) + i;")
+        s.append("  const double2* __restrict__ kp = reinterpret_cast<const double2*>(I.ket.prim) + j;")
         s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
         s.append("    const double2 q0 = __ldg(kp), q1 = __ldg(kp + nk), q2 = __ldg(kp + 2 * (size_t)nk);")
         s.append("    const double sQ = q0.x, UQ = q0.y, Qx = q1.x, Qy = q1.y, Qz = q2.x, kzQ = q2.y;")
@@ -316,16 +316,19 @@ class ClassGen:
         s.extend(self.tables())
         s.append("")
         s.append("template <int MODE>")
-        s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const PcEriArgs A) {" % (block, self.min_blocks(), self.name))
-        s.append("  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;")
+        s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const __grid_constant__ PcEriArgs A) {" % (block, self.min_blocks(), self.name))
+        s.append("  const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);")
+        s.append("  if (gw >= A.nwarps) return;")
+        s.append("  const PcItem& I = A.items[pc_find_item(A, gw)];")
+        s.append("  const long long t = (long long)(gw - I.warp0) * 32 + (threadIdx.x & 31);")
         s.append("  int i, j, seg_lo, seg_hi;")
-        s.append("  if (!pc_decode_task(A, t, i, j, seg_lo, seg_hi)) return;")
+        s.append("  if (!pc_decode_task(A, I, t, i, j, seg_lo, seg_hi)) return;")
         s.append("  // contraction depths after the primitive-pair cut-off (per shell pair)")
-        s.append("  const int nb = A.bra.n, nk = A.ket.n, KB = __ldg(A.bra.keff + i), KK = __ldg(A.ket.keff + j);")
+        s.append("  const int nb = I.bra.n, nk = I.ket.n, KB = __ldg(I.bra.keff + i), KK = __ldg(I.ket.keff + j);")
         s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
-        s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(A.bra.fx + i), __ldg(A.bra.fy + i), __ldg(A.ket.fx + j), __ldg(A.ket.fy + j));" % (NA, NB, NC, ND))
-        s.append("  const double AB0 = __ldg(A.bra.xy + i), AB1 = __ldg(A.bra.xy + nb + i), AB2 = __ldg(A.bra.xy + 2 * nb + i);")
-        s.append("  const double CD0 = __ldg(A.ket.xy + j), CD1 = __ldg(A.ket.xy + nk + j), CD2 = __ldg(A.ket.xy + 2 * nk + j);")
+        s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(I.bra.fx + i), __ldg(I.bra.fy + i), __ldg(I.ket.fx + j), __ldg(I.ket.fy + j));" % (NA, NB, NC, ND))
+        s.append("  const double AB0 = __ldg(I.bra.xy + i), AB1 = __ldg(I.bra.xy + nb + i), AB2 = __ldg(I.bra.xy + 2 * nb + i);")
+        s.append("  const double CD0 = __ldg(I.ket.xy + j), CD1 = __ldg(I.ket.xy + nk + j), CD2 = __ldg(I.ket.xy + 2 * nk + j);")
         s.append("  double acc[NE * NF];")
         s.append("#pragma unroll%s" % (" 1" if self.V2 else ""))
         s.append("  for (int k = 0; k < NE * NF; ++k) acc[k] = 0.0;")
@@ -339,14 +342,14 @@ class ClassGen:
         s.append("  double g[NSPH];")
         for line in tail:
             s.append("  " + line)
-        s.append("  pc_epilogue<MODE, %d, %d, %d, %d>(A, t, i, j, seg_lo, seg_hi, g);" % (NA, NB, NC, ND))
+        s.append("  pc_epilogue<MODE, %d, %d, %d, %d>(A, I, t, i, j, seg_lo, seg_hi, g);" % (NA, NB, NC, ND))
         s.append("}")
         s.append("}  // namespace")
         s.append("")
         s.append("cudaError_t pc_launch_%s(int mode, const PcEriArgs& A, cudaStream_t st) {" % self.name)
-        s.append("  if (A.t_count <= 0) return cudaSuccess;")
+        s.append("  if (A.nwarps <= 0) return cudaSuccess;")
         s.append("  const int block = %d;" % block)
-        s.append("  const unsigned grid = (unsigned)((A.t_count + block - 1) / block);")
+        s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
         for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL"):
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))

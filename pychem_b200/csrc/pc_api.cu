@@ -110,6 +110,13 @@ struct PlanItem {
   DevBuf<int>* warp_s0;
 };
 
+// the bucket pairs of one angular-momentum class that go into one fused kernel launch
+struct LaunchGroup {
+  int pcb, pck;
+  std::vector<int> items;   // indices into pc_basis::plan
+  double cost;
+};
+
 bool is_device_ptr(const void* p) {
   if (!p) return false;
   cudaPointerAttributes at;
@@ -318,6 +325,7 @@ struct pc_basis {
   double thresh = 0;
   int rank = 0, nranks = 1;
   std::vector<PlanItem> plan;
+  std::vector<LaunchGroup> groups;     // launch order (longest first)
   std::vector<DevBuf<long long>*> plan_bufs;
   std::vector<DevBuf<int>*> plan_ibufs;
   long long my_quartets = 0, my_eris = 0, all_quartets = 0, all_eris = 0;
@@ -437,17 +445,57 @@ int upload_kind(pc_basis* h, Kind* k) {
   return 0;
 }
 
-int launch_class(pc_basis* h, int mode, const Kind* kb, const Kind* kk, PcEriArgs& A,
-                 cudaStream_t st = nullptr) {
-  pc_launch_fn fn = pc_launch_table[kb->pc][kk->pc];
-  if (!fn) return fail("internal: no kernel for this class order");
-  A.bra = kb->view();
-  A.ket = kk->view();
+void fill_item(PcItem& I, const Kind* kb, const Kind* kk) {
+  memset(&I, 0, sizeof(I));
+  I.bra = kb->view();
+  I.ket = kk->view();
+}
+
+cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, cudaStream_t st) {
+  pc_launch_fn fn = pc_launch_table[pcb][pck];
+  if (!fn) return cudaErrorInvalidValue;
   A.boys = h->boys.p;
   A.nbf = h->nbf;
   cudaError_t e = fn(mode, A, st ? st : h->stream);
+  if (e == cudaSuccess) h->launches += 1;
+  return e;
+}
+
+// single bucket pair with an explicit (bra, ket) task list -- Schwarz diagonal, pc_eri_quartets
+int launch_explicit(pc_basis* h, int mode, const Kind* kb, const Kind* kk, PcEriArgs& A, const int* ex_bra,
+                    const int* ex_ket, long long count) {
+  fill_item(A.items[0], kb, kk);
+  A.items[0].t_count = count;
+  A.items[0].warp0 = 0;
+  A.nitems = 1;
+  A.nwarps = (int)((count + 31) / 32);
+  A.ex_bra = ex_bra;
+  A.ex_ket = ex_ket;
+  cudaError_t e = launch_args(h, mode, kb->pc, kk->pc, A, nullptr);
   if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
-  h->launches += 1;
+  return 0;
+}
+
+// one fused launch: all bucket pairs of one class (a LaunchGroup), every item warp-aligned
+int launch_group(pc_basis* h, int mode, const LaunchGroup& g, PcEriArgs& A, cudaStream_t st) {
+  int warp = 0, n = 0;
+  for (int idx : g.items) {
+    const PlanItem& it = h->plan[idx];
+    if (it.count == 0) continue;
+    PcItem& I = A.items[n++];
+    fill_item(I, h->kinds[it.kb], h->kinds[it.kk]);
+    I.seg_off = it.seg_off->p; I.seg_ij = (const int2*)it.seg_ij->p; I.warp_s0 = it.warp_s0->p;
+    I.nseg = it.nseg; I.t_begin = it.begin; I.t_count = it.count;
+    I.warp0 = warp;
+    warp += (int)((it.count + 31) / 32);
+  }
+  if (n == 0) return 0;
+  A.nitems = n;
+  A.nwarps = warp;
+  A.ex_bra = nullptr;
+  A.ex_ket = nullptr;
+  cudaError_t e = launch_args(h, mode, g.pcb, g.pck, A, st);
+  if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
   return 0;
 }
 
@@ -579,10 +627,8 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax) {
       PC_CUDA(dout.alloc((size_t)nb * nb * n));
       PcEriArgs A;
       memset(&A, 0, sizeof(A));
-      A.ex_bra = didx.p; A.ex_ket = didx.p;
-      A.t_begin = 0; A.t_count = n;
       A.out = dout.p;
-      if (launch_class(h, PC_MODE_BLOCKS, k, k, A)) return 1;
+      if (launch_explicit(h, PC_MODE_BLOCKS, k, k, A, didx.p, didx.p, n)) return 1;
       std::vector<double> out((size_t)nb * nb * n);
       PC_CUDA(cudaMemcpyAsync(out.data(), dout.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       PC_CUDA(cudaStreamSynchronize(h->stream));
@@ -724,11 +770,6 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     };
     parallel_for(work.size(), [&](size_t k) { build_segments(work[k]); });
     // ---- phase B: plan items + static multi-GPU schedule ---------------------
-    // cost model = flop model of the class.  Large bucket pairs are cut into nranks equal
-    // contiguous slices (cost inside a bucket pair is uniform -> exactly balanced).  The many
-    // small bucket pairs (the cheapest ones, together <= 15 % of the modelled cost) are NOT
-    // sliced -- a slice of a small launch does not fill a GPU -- but handed out whole, longest
-    // first, to the least loaded rank (LPT).
     std::vector<int> widx;       // work index of every plan item
     for (size_t k = 0; k < work.size(); ++k) {
       Work& w = work[k];
@@ -750,31 +791,12 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       return it.prim_exec * pc_flop_prim_table[B->pc][Kt->pc] +
              (double)it.total * (pc_flop_cont_table[B->pc][Kt->pc] + 40.0 * nsph + 60.0);
     };
-    {
-      std::vector<int> order(h->plan.size());
-      std::iota(order.begin(), order.end(), 0);
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-        return cost_total(h->plan[a]) > cost_total(h->plan[b]);
-      });
-      double all = 0;
-      for (const PlanItem& it : h->plan) all += cost_total(it);
-      std::vector<double> load(nranks, 0.0);
-      double cum = 0;
-      for (int idx : order) {
-        PlanItem& it = h->plan[idx];
-        const double c = cost_total(it);
-        cum += c;
-        const bool whole = nranks > 1 && cum > 0.85 * all;
-        if (!whole) {
-          it.begin = it.total * rank / nranks;
-          it.count = it.total * (rank + 1) / nranks - it.begin;
-        } else {
-          const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-          load[r] += c;
-          it.begin = 0;
-          it.count = (r == rank) ? it.total : 0;
-        }
-      }
+    // every bucket pair is cut into nranks equal contiguous slices: cost inside a bucket pair is
+    // uniform, so the schedule is exactly balanced; because all bucket pairs of a class share
+    // ONE fused launch, the slices of small bucket pairs cost nothing extra
+    for (PlanItem& it : h->plan) {
+      it.begin = it.total * rank / nranks;
+      it.count = it.total * (rank + 1) / nranks - it.begin;
     }
     // ---- phase C (host threads): segment of every warp's first task ------------------------
     parallel_for(h->plan.size(), [&](size_t k) {
@@ -811,12 +833,28 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       h->my_quartets += it.count; h->my_eris += it.count * nsph;
     }
     PC_CUDA(cudaStreamSynchronize(h->stream));      // host vectors in `work` die below
-    // longest-first launch order
-    auto cost = [&](const PlanItem& it) {
-      return it.total ? cost_total(it) * ((double)it.count / (double)it.total) : 0.0;
-    };
-    std::stable_sort(h->plan.begin(), h->plan.end(),
-                     [&](const PlanItem& a, const PlanItem& b) { return cost(a) > cost(b); });
+    // ---- launch groups: all bucket pairs of one class -> one fused launch, longest first ----
+    h->groups.clear();
+    {
+      std::map<std::pair<int, int>, std::vector<int>> by_class;
+      for (size_t k = 0; k < h->plan.size(); ++k)
+        by_class[{h->kinds[h->plan[k].kb]->pc, h->kinds[h->plan[k].kk]->pc}].push_back((int)k);
+      for (auto& kv : by_class) {
+        std::vector<int>& v = kv.second;
+        std::stable_sort(v.begin(), v.end(), [&](int a, int b) { return cost_total(h->plan[a]) > cost_total(h->plan[b]); });
+        for (size_t c0 = 0; c0 < v.size(); c0 += PC_MAX_ITEMS) {
+          LaunchGroup g;
+          g.pcb = kv.first.first; g.pck = kv.first.second; g.cost = 0;
+          for (size_t c = c0; c < std::min(v.size(), c0 + PC_MAX_ITEMS); ++c) {
+            g.items.push_back(v[c]);
+            g.cost += cost_total(h->plan[v[c]]);
+          }
+          h->groups.push_back(g);
+        }
+      }
+      std::stable_sort(h->groups.begin(), h->groups.end(),
+                       [](const LaunchGroup& a, const LaunchGroup& b) { return a.cost > b.cost; });
+    }
     h->planned = true;
     h->plan_id += 1;
     h->thresh = thresh; h->rank = rank; h->nranks = nranks;
@@ -861,8 +899,8 @@ int pc_eri_quartets(pc_basis* h, int n, const int* abcd, const long long* offset
     PC_CUDA(dout.alloc((size_t)nsph * m));
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.ex_bra = dbi.p; A.ex_ket = dkj.p; A.t_count = m; A.out = dout.p;
-    if (launch_class(h, PC_MODE_BLOCKS, B, Kt, A)) return 1;
+    A.out = dout.p;
+    if (launch_explicit(h, PC_MODE_BLOCKS, B, Kt, A, dbi.p, dkj.p, m)) return 1;
     std::vector<double> res((size_t)nsph * m);
     PC_CUDA(cudaMemcpyAsync(res.data(), dout.p, res.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     PC_CUDA(cudaStreamSynchronize(h->stream));
@@ -900,13 +938,11 @@ int pc_eri_tensor(pc_basis* h, double* G_dev, double* G_host) {
   PC_CUDA(cudaSetDevice(h->device));
   const size_t N = h->nbf, n4 = N * N * N * N;
   PC_CUDA(cudaMemsetAsync(G_dev, 0, n4 * sizeof(double), h->stream));
-  for (const PlanItem& it : h->plan) {
+  for (const LaunchGroup& g : h->groups) {
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.seg_off = it.seg_off->p; A.seg_ij = (const int2*)it.seg_ij->p; A.warp_s0 = it.warp_s0->p;
-    A.nseg = it.nseg; A.t_begin = it.begin; A.t_count = it.count;
     A.G = G_dev;
-    if (launch_class(h, PC_MODE_TENSOR, h->kinds[it.kb], h->kinds[it.kk], A)) return 1;
+    if (launch_group(h, PC_MODE_TENSOR, g, A, nullptr)) return 1;
   }
   if (G_host)
     PC_CUDA(cudaMemcpyAsync(G_host, G_dev, n4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -971,7 +1007,7 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
       stage_in(h, Db, h->dstage.p + 2 * nn, &db)) return 1;
   pc_basis::GraphKey key;
   key.variant = variant; key.dt = dt; key.da = da; key.db = db; key.acc = acc_dev; key.plan_id = h->plan_id;
-  const bool graphs = h->use_graphs && !h->profiling && h->plan.size() > 1;
+  const bool graphs = h->use_graphs && !h->profiling && h->groups.size() > 1;
   if (graphs && h->graph_exec && key == h->graph_key) {
     PC_CUDA(cudaGraphLaunch(h->graph_exec, h->stream));
     h->launches += h->graph_launches;
@@ -981,7 +1017,7 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
   if (graphs) PC_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
   PC_CUDA(cudaMemsetAsync(acc_dev, 0, 3 * nn * sizeof(double), h->stream));
   if (h->profiling) {
-    while (h->prof_events.size() < h->plan.size() + 1) {
+    while (h->prof_events.size() < h->groups.size() + 1) {
       cudaEvent_t e;
       PC_CUDA(cudaEventCreate(&e));
       h->prof_events.push_back(e);
@@ -992,7 +1028,7 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
     const int v = e ? atoi(e) : 8;
     return v < 1 ? 1 : (v > 64 ? 64 : v);
   }();
-  const bool fan = !h->profiling && h->plan.size() > 1;
+  const bool fan = !h->profiling && h->groups.size() > 1;
   if (fan) {
     while ((int)h->side.size() < NSIDE) {
       cudaStream_t st;
@@ -1007,19 +1043,15 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
     for (int s2 = 0; s2 < NSIDE; ++s2) PC_CUDA(cudaStreamWaitEvent(h->side[s2], h->ev_fork, 0));
   }
   size_t idx = 0;
-  for (const PlanItem& it : h->plan) {
+  for (const LaunchGroup& g : h->groups) {
     if (h->profiling) PC_CUDA(cudaEventRecord(h->prof_events[idx], h->stream));
     ++idx;
-    if (it.count == 0) continue;
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
-    A.seg_off = it.seg_off->p; A.seg_ij = (const int2*)it.seg_ij->p; A.warp_s0 = it.warp_s0->p;
-    A.nseg = it.nseg; A.t_begin = it.begin; A.t_count = it.count;
     A.Dj = dt; A.Da = da; A.Db = db;
     A.Jacc = acc_dev; A.Kaacc = acc_dev + nn; A.Kbacc = acc_dev + 2 * nn;
     A.out = acc_dev;
-    if (launch_class(h, variant, h->kinds[it.kb], h->kinds[it.kk], A,
-                     fan ? h->side[idx % NSIDE] : h->stream)) return 1;
+    if (launch_group(h, variant, g, A, fan ? h->side[idx % NSIDE] : h->stream)) return 1;
   }
   if (fan) {
     for (int s2 = 0; s2 < NSIDE; ++s2) {
@@ -1042,9 +1074,13 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
   if (h->profiling) {
     PC_CUDA(cudaEventRecord(h->prof_events[idx], h->stream));
     PC_CUDA(cudaStreamSynchronize(h->stream));
+    // one fused launch per group: its time is booked on the group's first bucket pair
     h->prof_ms.assign(h->plan.size(), 0.f);
-    for (size_t k = 0; k < h->plan.size(); ++k)
-      PC_CUDA(cudaEventElapsedTime(&h->prof_ms[k], h->prof_events[k], h->prof_events[k + 1]));
+    for (size_t k = 0; k < h->groups.size(); ++k) {
+      float ms = 0.f;
+      PC_CUDA(cudaEventElapsedTime(&ms, h->prof_events[k], h->prof_events[k + 1]));
+      if (!h->groups[k].items.empty()) h->prof_ms[h->groups[k].items[0]] = ms;
+    }
   }
   return 0;
 }

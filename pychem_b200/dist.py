@@ -32,10 +32,9 @@ def init(backend=None):
 
 def slice_bounds(total, rank, nranks):
     """This rank's contiguous slice [begin, end) of a bucket pair's `total` tasks -- the same
-    arithmetic pc_plan (csrc/pc_api.cu) applies to every LARGE bucket pair (cost inside a bucket
-    pair is uniform, so equal slices are exactly balanced); the cheapest bucket pairs (<= 15 % of
-    the modelled cost) are handed out whole by LPT instead, so no rank gets launches too small to
-    fill a GPU."""
+    arithmetic pc_plan (csrc/pc_api.cu) applies to every bucket pair (cost inside a bucket pair
+    is uniform, so equal slices are an exactly balanced static schedule; the slices of all
+    bucket pairs of a class run in one fused launch)."""
     begin = total * rank // nranks
     end = total * (rank + 1) // nranks
     return begin, end
