@@ -23,6 +23,7 @@ LIB = os.path.join(HERE, "libpychem_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177", "-diag-suppress", "550"]
+NVCC_FLAGS += os.environ.get("PYCHEM_B200_NVCC_EXTRA", "").split()     # experiments only
 
 
 def _hash(paths, extra=""):
