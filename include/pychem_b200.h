@@ -112,6 +112,10 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
                             const double* Db, double* acc_dev);
 int pc_jk_finalize(pc_basis* h, int variant, const double* acc_dev, double* J, double* Xa,
                    double* Xb);
+/* pc_jk_classify + pc_jk_direct_accumulate with a single upload of host densities; *variant
+ * receives the variant that was used (pass it to pc_jk_finalize). */
+int pc_jk_direct_accumulate_auto(pc_basis* h, const double* Dt, const double* Da, const double* Db,
+                                 double* acc_dev, int* variant);
 int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
                  double* J, double* Xa, double* Xb);
 /* variant (PC_JK_RHF/UHF/GEN) the densities allow: symmetric & Da==Db / symmetric / general.

@@ -29,6 +29,7 @@ SIGNATURES = {
     "pc_jk_stored": [c_vp] + [c_vp] * 7,
     "pc_jk_direct_accumulate": [c_vp, ctypes.c_int] + [c_vp] * 4,
     "pc_jk_finalize": [c_vp, ctypes.c_int] + [c_vp] * 4,
+    "pc_jk_direct_accumulate_auto": [c_vp, c_vp, c_vp, c_vp, c_vp, c_ip],
     "pc_jk_direct": [c_vp, ctypes.c_int] + [c_vp] * 6,
     "pc_jk_classify": [c_vp, c_vp, c_vp, c_vp, c_ip],
     "pc_launch_count": [c_vp, c_llp],

@@ -1154,6 +1154,20 @@ int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double
   return 0;
 }
 
+int pc_jk_direct_accumulate_auto(pc_basis* h, const double* Dt, const double* Da, const double* Db,
+                                 double* acc_dev, int* variant) {
+  if (!h || !variant) return fail("pc_jk_direct_accumulate_auto: null");
+  PC_CUDA(cudaSetDevice(h->device));
+  if (ensure_scratch(h)) return 1;
+  // classify on the device, then digest straight from the staged copies (one upload only)
+  if (pc_jk_classify(h, Dt, Da, Db, variant)) return 1;
+  const size_t nn = (size_t)h->nbf * h->nbf;
+  if (!is_device_ptr(Dt)) Dt = h->dstage.p;
+  if (!is_device_ptr(Da)) Da = h->dstage.p + nn;
+  if (Db && !is_device_ptr(Db)) Db = h->dstage.p + 2 * nn;
+  return pc_jk_direct_accumulate(h, *variant, Dt, Da, Db, acc_dev);
+}
+
 int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
                  double* J, double* Xa, double* Xb) {
   if (!h) return fail("pc_jk_direct: null");

@@ -192,13 +192,8 @@ class DeviceBasis:
         Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
         if self.counts is None:
             self.plan()
-        if variant is None:
-            if self.counts["nranks"] == 1:
-                variant = AUTO                      # classified on the device inside pc_jk_direct
-            else:
-                v = ctypes.c_int()
-                _lib.check(self.lib.pc_jk_classify(self.h, _ptr(Dt), _ptr(Da), _ptr(Db), ctypes.byref(v)))
-                variant = v.value
+        if variant is None and self.counts["nranks"] == 1:
+            variant = AUTO                          # classified on the device inside pc_jk_direct
         J, Xa, Xb = self._outputs(Dt)
         if self.counts["nranks"] == 1:
             _lib.check(self.lib.pc_jk_direct(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db),
@@ -207,7 +202,13 @@ class DeviceBasis:
         import torch
         import torch.distributed as dist
         acc = self.accumulator()
-        _lib.check(self.lib.pc_jk_direct_accumulate(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db), _ptr(acc)))
+        if variant is None:
+            v = ctypes.c_int()
+            _lib.check(self.lib.pc_jk_direct_accumulate_auto(self.h, _ptr(Dt), _ptr(Da), _ptr(Db), _ptr(acc),
+                                                             ctypes.byref(v)))
+            variant = v.value
+        else:
+            _lib.check(self.lib.pc_jk_direct_accumulate(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db), _ptr(acc)))
         # the library launched on its own stream: order the collective after it
         ev = torch.cuda.Event()
         ev.record(self.torch_stream())

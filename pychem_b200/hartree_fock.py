@@ -60,7 +60,16 @@ def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
         st["G_dev"] = G_dev
         molecule.CoulombIntegrals = G_host
     else:
-        db.plan(engine.INTEGRAL_THRESHOLD, 0, 1)
+        # one process per GPU: every rank keeps its slice of the quartet schedule and the partial
+        # J/K are all-reduced inside make_coulomb_exchange_matrices (engine.DeviceBasis.jk_direct)
+        rank, world = 0, 1
+        try:
+            import torch.distributed as tdist
+            if tdist.is_available() and tdist.is_initialized():
+                rank, world = tdist.get_rank(), tdist.get_world_size()
+        except ImportError:
+            pass
+        db.plan(engine.INTEGRAL_THRESHOLD, rank, world)
         molecule.CoulombIntegrals = None
     _STATE[id(molecule)] = st
 
