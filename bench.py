@@ -404,24 +404,25 @@ def run_b200(args):
     eri_ms = sum(v["ms"] for v in per_class.values())
     achieved = all_flops / (ms_step * 1e-3) / 1e12 / world      # per-GPU TFLOP/s over the whole step
     # dominant kernel = the class kernel with the largest share of the step (per-launch CUDA-event
-    # times of one profiled build).  `traffic`: DRAM bytes of its largest launch from the committed
-    # ncu --set full capture (profiles/r1_final_ncu_full_eri_psss_jk.txt) -- everything is
+    # times of one profiled build).  `traffic`: DRAM bytes of its (fused) launch from the committed
+    # ncu --set full capture (profiles/r1_final_ncu_full_fused_top4.txt) -- everything is
     # L2-resident, the path is not HBM-bound.
     top_tf = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 if top[1]["ms"] else None
     roofline = {"bound": "fp64", "achieved": top_tf, "peak": peak, "unit": "TFLOP/s",
                 "frac": (top_tf / peak) if (top_tf and peak) else None,
-                "traffic": 19.4e6 if top[0] == "psss" else None,
-                "kernel": "eri_%s_kernel<JK_RHF>: %d launches per build (one per bucket pair), %.3f ms "
-                          "serialised, %.1f%% of the serialised per-class total"
+                "traffic": 87.2e6 if top[0] == "psss" else None,
+                "kernel": "eri_%s_kernel<JK_RHF>: one fused launch per build covering its %d bucket pairs, %.3f ms "
+                          "alone, %.1f%% of the serialised per-class total"
                           % (top[0], sum(1 for c in db.plan_items()[0] if "spd"[c[0]] + "spd"[c[1]] + "spd"[c[2]] + "spd"[c[3]] == top[0]),
                              top[1]["ms"], 100.0 * top[1]["ms"] / eri_ms if eri_ms else 0.0),
                 "peak_source": "pc_fp64_peak: register-resident DFMA loop measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the longest launch, ncu --set full, "
-                                  "profiles/r1_final_ncu_full_eri_psss_jk.txt",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the fused eri_psss launch, ncu --set "
+                                  "full, profiles/r1_final_ncu_full_fused_top4.txt (pair tables, Boys table, densities "
+                                  "and accumulators are L2-resident: the kernel is LSU/atomic-bound, not HBM-bound)",
                 "whole_step": {"achieved": achieved, "frac": achieved / peak if peak else None,
-                               "kernels": "all %d eri_*_kernel<JK_RHF> launches of one Fock build, concurrent on 8 "
-                                          "streams, replayed as one CUDA graph" % launches,
+                               "kernels": "all %d launches of one Fock build (21 eri_*_kernel<JK_RHF> + finalize), concurrent "
+                                          "on 8 streams, replayed as one CUDA graph" % launches,
                                "algorithmic_gflop_per_step": all_flops / 1e9,
                                "reference_unscreened_gflop_per_step": ref_flops / 1e9,
                                "serialised_kernel_ms_over_step_ms": eri_ms / ms_step if ms_step else None},
