@@ -147,6 +147,11 @@ __global__ void mp2_opp_spin_kernel(int noa, int nva, int nob, int nvb, const do
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+struct StreamGuard {
+  cudaStream_t st = nullptr;
+  ~StreamGuard() { if (st) cudaStreamDestroy(st); }
+};
+
 struct Buf {
   double* p = nullptr;
   cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(double)); }
@@ -182,8 +187,9 @@ int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, cons
   if (N <= 0 || na < 0 || nb < 0 || na > N || nb > N) return mp2_fail("pc_mp2_energy: bad sizes");
   if ((long long)N * N * N > 2147483647LL) return mp2_fail("pc_mp2_energy: N too large for this build");
   MP2_CUDA(cudaSetDevice(device));
-  cudaStream_t st;
-  MP2_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  StreamGuard guard;
+  MP2_CUDA(cudaStreamCreateWithFlags(&guard.st, cudaStreamNonBlocking));
+  cudaStream_t st = guard.st;
   const size_t NN = (size_t)N * N;
   Buf dCa, dCb, dEa, dEb, T1, T2, T3, T4, out;
   MP2_CUDA(dCa.alloc(NN)); MP2_CUDA(dCb.alloc(NN)); MP2_CUDA(dEa.alloc(N)); MP2_CUDA(dEb.alloc(N));
@@ -217,7 +223,6 @@ int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, cons
   double res[3];
   MP2_CUDA(cudaMemcpyAsync(res, out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   MP2_CUDA(cudaStreamSynchronize(st));
-  cudaStreamDestroy(st);
   *Eaa = res[0]; *Eab = res[1]; *Ebb = res[2];
   return 0;
 }

@@ -72,6 +72,24 @@ def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
         db.plan(engine.INTEGRAL_THRESHOLD, rank, world)
         molecule.CoulombIntegrals = None
     _STATE[id(molecule)] = st
+    _evict_other_molecules(molecule)
+
+
+def _evict_other_molecules(molecule, keep=2):
+    """The dense tensor of one molecule can be tens of GB of HBM: keep device state only for the
+    `keep` most recently evaluated molecules (pychem.main walks the input sections one by one)."""
+    order = _STATE.setdefault("__order__", [])
+    key = id(molecule)
+    if key in order:
+        order.remove(key)
+    order.append(key)
+    while len(order) > keep:
+        old = order.pop(0)
+        st = _STATE.pop(old, None)
+        if st is not None:
+            st["G_dev"] = None
+            from . import integrals
+            integrals.release(st["molecule"])
 
 
 def make_coulomb_exchange_matrices(molecule, this):
@@ -109,6 +127,8 @@ def install(reference_hartree_fock, reference_noci=None):
 
 
 def release(molecule=None):
-    keys = list(_STATE) if molecule is None else [id(molecule)]
+    keys = [k for k in _STATE if k != "__order__"] if molecule is None else [id(molecule)]
     for k in keys:
         _STATE.pop(k, None)
+        if k in _STATE.get("__order__", []):
+            _STATE["__order__"].remove(k)

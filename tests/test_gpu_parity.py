@@ -230,3 +230,38 @@ def test_full_size_linearity_symmetry_partition(eng, water8):
     assert np.abs(J - J1).max() < 1e-10 * scale
     assert np.abs(Xa - X1).max() < 1e-10 * scale
     db.plan(1.0e-8, 0, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# other basis sets / elements: contraction depths and shell mixes the water tests do not have
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("basis,coords", [
+    ("STO-3G", [["C", 6.0, 0.0, 0.0, 0.0], ["O", 8.0, 0.0, 0.0, 1.13]]),
+    ("3-21G", [["N", 7.0, 0.0, 0.0, 0.12], ["H", 1.0, 0.0, 0.94, -0.27], ["H", 1.0, 0.81, -0.47, -0.27],
+               ["H", 1.0, -0.81, -0.47, -0.27]]),
+    ("6-311G**", [["F", 9.0, 0.0, 0.0, 0.0], ["H", 1.0, 0.0, 0.0, 0.92]]),
+    ("cc-pVDZ", [["O", 8.0, 0.0, 0.0, 0.117790], ["H", 1.0, 0.0, 0.755453, -0.471161],
+                 ["H", 1.0, 0.0, -0.755453, -0.471161]]),
+    ("6-31G*", [["Li", 3.0, 0.0, 0.0, 0.0], ["F", 9.0, 0.0, 0.0, 1.56]]),
+])
+def test_other_basis_sets_vs_oracle(eng, basis, coords):
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    mol = S.Molecule(coords, basis)
+    db = eng.DeviceBasis(mol)
+    bounds, _ = db.schwarz()
+    ob = oracle.OracleBasis(db.table)
+    ob_bounds, _ = ob.schwarz()
+    assert np.abs(bounds - ob_bounds).max() < 1e-12
+    G_dev, G = db.eri_tensor(1.0e-8, to_host=True)
+    G_ref, _ = ob.tensor(1.0e-8)
+    assert np.abs(G - G_ref).max() < ERI_TOL
+    rng = np.random.default_rng(9)
+    N = db.nbf
+    A, B = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    ref = oracle.jk(G_ref, A + B, A, B)
+    db.plan(1.0e-8, 0, 1)
+    for got in (db.jk_stored(G_dev, A + B, A, B), db.jk_direct(A + B, A, B)):
+        for mine, r in zip(got, ref):
+            assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
+    db.close()
