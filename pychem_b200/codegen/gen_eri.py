@@ -82,6 +82,21 @@ def c2s_rows(l):
     raise ValueError(l)
 
 
+def nfun(l, cart_d=False):
+    """functions per shell: 2l+1 real spherical, or the 6 Cartesians for d when Cartesian_L = [2]
+    (Util/structures.py:844-849)."""
+    return ncart(l) if (cart_d and l == 2) else nsph(l)
+
+
+def c2s_rows_any(l, cart_d=False):
+    """cart->function rows incl. the component-dependent normalisation ratio.  Cartesian d keeps
+    all six components (CartToSpher = identity) and only carries nm_xx/nm_xy = 1/sqrt(3)."""
+    if cart_d and l == 2:
+        r3 = 1.0 / math.sqrt(3.0)
+        return [[(0, r3)], [(1, 1.0)], [(2, 1.0)], [(3, r3)], [(4, 1.0)], [(5, r3)]]
+    return c2s_rows(l)
+
+
 class Emit:
     def __init__(self, prefix):
         self.lines = []
@@ -119,16 +134,18 @@ def lin_comb(em, terms):
 
 
 class ClassGen:
-    def __init__(self, lx1, ly1, lx2, ly2):
+    def __init__(self, lx1, ly1, lx2, ly2, cart_d=False):
         self.l = (lx1, ly1, lx2, ly2)
+        self.cart_d = bool(cart_d) and 2 in self.l
         self.La, self.Lc = lx1 + ly1, lx2 + ly2
         self.L = self.La + self.Lc
-        self.name = "".join(LNAME[x] for x in self.l)
+        names = "spDf" if self.cart_d else LNAME
+        self.name = "".join(names[x] for x in self.l)
         # contracted (e0|f0): e = lx1..La, f = lx2..Lc, all components
         self.e_list = [c for le in range(lx1, self.La + 1) for c in comps(le)]
         self.f_list = [c for lf in range(lx2, self.Lc + 1) for c in comps(lf)]
         self.ne, self.nf = len(self.e_list), len(self.f_list)
-        self.nsph = [nsph(x) for x in self.l]
+        self.nsph = [nfun(x, self.cart_d) for x in self.l]
 
     # ------------------------------------------------------------------ VRR
     def gen_vrr(self):
@@ -188,7 +205,7 @@ class ClassGen:
         self.c2s_ops = 0
         f_index = {c: i for i, c in enumerate(self.f_list)}
         e_index = {c: i for i, c in enumerate(self.e_list)}
-        nqs = nsph(lx2) * nsph(ly2)
+        nqs = nfun(lx2, self.cart_d) * nfun(ly2, self.cart_d)
 
         # ---- ket HRR for every bra e-component, then ket cart->sph
         ks = {}     # (ie, q) -> var
@@ -213,11 +230,11 @@ class ClassGen:
             # transform second index then first
             half = {}
             for ix in range(ncart(lx2)):
-                for my, row in enumerate(c2s_rows(ly2)):
+                for my, row in enumerate(c2s_rows_any(ly2, self.cart_d)):
                     half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
-            for mx, row in enumerate(c2s_rows(lx2)):
-                for my in range(nsph(ly2)):
-                    ks[(ie, mx * nsph(ly2) + my)] = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
+            for mx, row in enumerate(c2s_rows_any(lx2, self.cart_d)):
+                for my in range(nfun(ly2, self.cart_d)):
+                    ks[(ie, mx * nfun(ly2, self.cart_d) + my)] = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
 
         # ---- bra HRR for every ket spherical component, then bra cart->sph
         out = []
@@ -241,12 +258,12 @@ class ClassGen:
             cart = {(ix, iy): hb(cx, cy) for ix, cx in enumerate(comps(lx1)) for iy, cy in enumerate(comps(ly1))}
             half = {}
             for ix in range(ncart(lx1)):
-                for my, row in enumerate(c2s_rows(ly1)):
+                for my, row in enumerate(c2s_rows_any(ly1, self.cart_d)):
                     half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
-            for mx, row in enumerate(c2s_rows(lx1)):
-                for my in range(nsph(ly1)):
+            for mx, row in enumerate(c2s_rows_any(lx1, self.cart_d)):
+                for my in range(nfun(ly1, self.cart_d)):
                     v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
-                    p = mx * nsph(ly1) + my
+                    p = mx * nfun(ly1, self.cart_d) + my
                     out.append("g[%d] = %s;" % (p * nqs + q, v))
         self.n_tail = em.n
         self.c2s_ops = em.ops
@@ -379,8 +396,8 @@ class ClassGenV2(ClassGen):
     thousands of live values) makes ptxas fall back to spilling everything."""
     V2 = True
 
-    def __init__(self, *cls):
-        ClassGen.__init__(self, *cls)
+    def __init__(self, *cls, **kw):
+        ClassGen.__init__(self, *cls, **kw)
         self.layout()
 
     def shell_needs(self):
@@ -542,8 +559,8 @@ class ClassGenV2(ClassGen):
         self.c2s_ops = 0
         f_index = {c: i for i, c in enumerate(self.f_list)}
         e_index = {c: i for i, c in enumerate(self.e_list)}
-        nqs = nsph(lx2) * nsph(ly2)
-        nps = nsph(lx1) * nsph(ly1)
+        nqs = nfun(lx2, self.cart_d) * nfun(ly2, self.cart_d)
+        nps = nfun(lx1, self.cart_d) * nfun(ly1, self.cart_d)
         lines = ["double ks[%d];" % (self.ne * nqs)]
         # ---- ket HRR + cart->sph, rolled over the bra (e0| component
         em = Emit("hk")
@@ -566,13 +583,13 @@ class ClassGenV2(ClassGen):
         cart = {(ix, iy): hk(cx, cy) for ix, cx in enumerate(comps(lx2)) for iy, cy in enumerate(comps(ly2))}
         half = {}
         for ix in range(ncart(lx2)):
-            for my, row in enumerate(c2s_rows(ly2)):
+            for my, row in enumerate(c2s_rows_any(ly2, self.cart_d)):
                 half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
         outs = []
-        for mx, row in enumerate(c2s_rows(lx2)):
-            for my in range(nsph(ly2)):
+        for mx, row in enumerate(c2s_rows_any(lx2, self.cart_d)):
+            for my in range(nfun(ly2, self.cart_d)):
                 v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
-                outs.append("ks[ie * %d + %d] = %s;" % (nqs, mx * nsph(ly2) + my, v))
+                outs.append("ks[ie * %d + %d] = %s;" % (nqs, mx * nfun(ly2, self.cart_d) + my, v))
         lines.append("#pragma unroll 1")
         lines.append("for (int ie = 0; ie < %d; ++ie) {" % self.ne)
         lines.append("  const double* __restrict__ ar = acc + ie * %d;" % self.nf)
@@ -601,13 +618,13 @@ class ClassGenV2(ClassGen):
         cart = {(ix, iy): hb(cx, cy) for ix, cx in enumerate(comps(lx1)) for iy, cy in enumerate(comps(ly1))}
         half = {}
         for ix in range(ncart(lx1)):
-            for my, row in enumerate(c2s_rows(ly1)):
+            for my, row in enumerate(c2s_rows_any(ly1, self.cart_d)):
                 half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
         outs = []
-        for mx, row in enumerate(c2s_rows(lx1)):
-            for my in range(nsph(ly1)):
+        for mx, row in enumerate(c2s_rows_any(lx1, self.cart_d)):
+            for my in range(nfun(ly1, self.cart_d)):
                 v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
-                outs.append("g[%d + q] = %s;" % ((mx * nsph(ly1) + my) * nqs, v))
+                outs.append("g[%d + q] = %s;" % ((mx * nfun(ly1, self.cart_d) + my) * nqs, v))
         lines.append("#pragma unroll 1")
         lines.append("for (int q = 0; q < %d; ++q) {" % nqs)
         lines.append("  const double* __restrict__ kr = ks + q;")
@@ -621,12 +638,12 @@ class ClassGenV2(ClassGen):
 V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
 
 
-def make_class(cls):
-    g = ClassGen(*cls)
+def make_class(cls, cart_d=False):
+    g = ClassGen(*cls, cart_d=cart_d)
     g.gen_vrr()
     if g.n_vrr > V2_THRESHOLD:
-        return ClassGenV2(*cls)
-    return ClassGen(*cls)
+        return ClassGenV2(*cls, cart_d=cart_d)
+    return ClassGen(*cls, cart_d=cart_d)
 
 
 def flop_model(g):
@@ -658,27 +675,40 @@ def main(outdir):
     os.makedirs(outdir, exist_ok=True)
     names = []
     model = {}
-    for cls in all_classes():
-        g = make_class(cls)
-        path = os.path.join(outdir, "eri_%s.cu" % g.name)
-        src = g.source()
-        model[g.name] = flop_model(g)
-        if not os.path.exists(path) or open(path).read() != src:
-            with open(path, "w") as fh:
-                fh.write(src)
-        names.append(g.name)
-        print("%s: %d vrr temps, %d tail temps, %d lines" % (g.name, g.n_vrr, g.n_tail, src.count("\n")))
-    # dispatch table
+    gens = {}
+    for cart in (False, True):
+        for cls in all_classes():
+            if cart and 2 not in cls:
+                continue                      # no d shell: the spherical kernel is the kernel
+            g = make_class(cls, cart_d=cart)
+            path = os.path.join(outdir, "eri_%s.cu" % g.name)
+            src = g.source()
+            if not cart:
+                model[g.name] = flop_model(g)
+            if not os.path.exists(path) or open(path).read() != src:
+                with open(path, "w") as fh:
+                    fh.write(src)
+            names.append(g.name)
+            gens[(cart, cls)] = g
+            print("%s: %d vrr temps, %d tail temps, %d lines" % (g.name, g.n_vrr, g.n_tail, src.count("\n")))
+    # dispatch tables
     tab = ['// GENERATED by pychem_b200/codegen/gen_eri.py -- do not edit.', '#include "../pc_common.cuh"']
     for n in names:
         tab.append("cudaError_t pc_launch_%s(int mode, const PcEriArgs& A, cudaStream_t st);" % n)
-    tab.append("// index [bra pair class][ket pair class], pair classes ss ps pp ds dp dd, bra >= ket")
-    tab.append("pc_launch_fn pc_launch_table[6][6] = {")
-    for ib, b in enumerate(PAIR_CLASSES):
-        row = []
-        for ik, k in enumerate(PAIR_CLASSES):
-            row.append("pc_launch_%s" % "".join(LNAME[x] for x in b + k) if ik <= ib else "nullptr")
-        tab.append("  {" + ", ".join(row) + "},")
+    tab.append("// index [d shells Cartesian?][bra pair class][ket pair class], pair classes ss ps pp ds dp dd, bra >= ket")
+    tab.append("pc_launch_fn pc_launch_table[2][6][6] = {")
+    for cart in (False, True):
+        tab.append(" {")
+        for ib, b in enumerate(PAIR_CLASSES):
+            row = []
+            for ik, k in enumerate(PAIR_CLASSES):
+                if ik <= ib:
+                    g = gens.get((cart, b + k)) or gens[(False, b + k)]
+                    row.append("pc_launch_%s" % g.name)
+                else:
+                    row.append("nullptr")
+            tab.append("  {" + ", ".join(row) + "},")
+        tab.append(" },")
     tab.append("};")
     for key, label in (("flop_prim", "pc_flop_prim_table"), ("flop_cont", "pc_flop_cont_table")):
         tab.append("double %s[6][6] = {" % label)
@@ -688,12 +718,19 @@ def main(outdir):
                 row.append(str(float(model["".join(LNAME[x] for x in b + k)][key])) if ik <= ib else "0.0")
             tab.append("  {" + ", ".join(row) + "},")
         tab.append("};")
-    tab.append("int pc_block_table[6][6] = {")
-    for ib, b in enumerate(PAIR_CLASSES):
-        row = []
-        for ik, k in enumerate(PAIR_CLASSES):
-            row.append(str(make_class(b + k).block_size()) if ik <= ib else "0")
-        tab.append("  {" + ", ".join(row) + "},")
+    tab.append("int pc_block_table[2][6][6] = {")
+    for cart in (False, True):
+        tab.append(" {")
+        for ib, b in enumerate(PAIR_CLASSES):
+            row = []
+            for ik, k in enumerate(PAIR_CLASSES):
+                if ik <= ib:
+                    g = gens.get((cart, b + k)) or gens[(False, b + k)]
+                    row.append(str(g.block_size()))
+                else:
+                    row.append("0")
+            tab.append("  {" + ", ".join(row) + "},")
+        tab.append(" },")
     tab.append("};")
     import json
     mpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data", "flop_model.json")
@@ -706,6 +743,11 @@ def main(outdir):
     if not os.path.exists(path) or open(path).read() != src:
         with open(path, "w") as fh:
             fh.write(src)
+    # stale files of classes that no longer exist would still be compiled: remove them
+    keep = set("eri_%s.cu" % n for n in names) | {"dispatch.cu"}
+    for f in os.listdir(outdir):
+        if f.endswith(".cu") and f not in keep:
+            os.remove(os.path.join(outdir, f))
     return names
 
 

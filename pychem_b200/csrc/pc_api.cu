@@ -313,6 +313,8 @@ struct pc_basis {
   int device = 0;
   cudaStream_t stream = nullptr;
   int nshell = 0, nbf = 0;
+  bool cart_d = false;                  // d shells carry their 6 Cartesians (Cartesian_L = [2])
+  int nfun(int l) const { return (l == 2 && cart_d) ? 6 : 2 * l + 1; }
   std::vector<Shell> shells;
   std::vector<double> exps, scc;
   std::vector<HostPair> pairs;  // upper-triangular order
@@ -452,7 +454,7 @@ void fill_item(PcItem& I, const Kind* kb, const Kind* kk) {
 }
 
 cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, cudaStream_t st) {
-  pc_launch_fn fn = pc_launch_table[pcb][pck];
+  pc_launch_fn fn = pc_launch_table[h->cart_d ? 1 : 0][pcb][pck];
   if (!fn) return cudaErrorInvalidValue;
   A.boys = h->boys.p;
   A.nbf = h->nbf;
@@ -535,13 +537,18 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return fail(cudaGetErrorString(e)); }
   h->nshell = nshell;
-  int poff = 0;
+  int poff = 0, n_d = 0;
   for (int s = 0; s < nshell; ++s) {
     if (l[s] < 0 || l[s] > 2) { delete h; return fail("pc_basis_create: only s, p, d shells are supported by this build"); }
-    if (l[s] >= 2 && is_cart[s]) { delete h; return fail("pc_basis_create: Cartesian d shells (Cartesian_L) are not supported by this build"); }
+    if (l[s] == 2) {
+      // Cartesian_L = [2] (Util/structures.py:844-849) applies to every d shell of the molecule
+      if (n_d == 0) h->cart_d = is_cart[s] != 0;
+      else if (h->cart_d != (is_cart[s] != 0)) { delete h; return fail("pc_basis_create: mixed Cartesian and spherical d shells are not supported"); }
+      ++n_d;
+    }
     if (K[s] <= 0) { delete h; return fail("pc_basis_create: empty contraction"); }
     Shell sh;
-    sh.l = l[s]; sh.K = K[s]; sh.first_fn = first_fn[s]; sh.nfn = 2 * l[s] + 1; sh.poff = poff;
+    sh.l = l[s]; sh.K = K[s]; sh.first_fn = first_fn[s]; sh.nfn = (l[s] == 2 && is_cart[s]) ? 6 : 2 * l[s] + 1; sh.poff = poff;
     for (int c = 0; c < 3; ++c) sh.A[c] = centres[3 * s + c];
     poff += K[s];
     h->shells.push_back(sh);
@@ -618,7 +625,7 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax) {
     h->bounds.assign(npair * 49, 0.0);
     for (Kind* k : h->kinds) {
       const int n = (int)k->pairs.size();
-      const int nx = 2 * k->lx + 1, ny = 2 * k->ly + 1, nb = nx * ny;
+      const int nx = h->nfun(k->lx), ny = h->nfun(k->ly), nb = nx * ny;
       std::vector<int> idx(n);
       std::iota(idx.begin(), idx.end(), 0);
       DevBuf<int> didx;
@@ -787,7 +794,7 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     auto cost_total = [&](const PlanItem& it) {
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
-      const double nsph = (2.0 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
+      const double nsph = (double)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);
       return it.prim_exec * pc_flop_prim_table[B->pc][Kt->pc] +
              (double)it.total * (pc_flop_cont_table[B->pc][Kt->pc] + 40.0 * nsph + 60.0);
     };
@@ -828,7 +835,7 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         PC_CUDA(it.seg_ij->upload(w.ij, h->stream));
         PC_CUDA(it.warp_s0->upload(w.s0, h->stream));
       }
-      const long long nsph = (long long)(2 * B->lx + 1) * (2 * B->ly + 1) * (2 * Kt->lx + 1) * (2 * Kt->ly + 1);
+      const long long nsph = (long long)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);
       h->all_quartets += it.total; h->all_eris += it.total * nsph;
       h->my_quartets += it.count; h->my_eris += it.count * nsph;
     }
@@ -890,7 +897,7 @@ int pc_eri_quartets(pc_basis* h, int n, const int* abcd, const long long* offset
     const Kind* Kt = h->kinds[kv.first.second];
     Grp& g = kv.second;
     const int m = (int)g.q.size();
-    const int n1 = 2 * B->lx + 1, n2 = 2 * B->ly + 1, n3 = 2 * Kt->lx + 1, n4 = 2 * Kt->ly + 1;
+    const int n1 = h->nfun(B->lx), n2 = h->nfun(B->ly), n3 = h->nfun(Kt->lx), n4 = h->nfun(Kt->ly);
     const int nsph = n1 * n2 * n3 * n4;
     DevBuf<int> dbi, dkj;
     DevBuf<double> dout;

@@ -122,3 +122,14 @@ def test_lih_chain_sfs_noci(patched, gold, tmp_path, k):
         # "ground state" 1.1 Eh below Hartree-Fock); its roots amplify rounding noise, so only the
         # Hamiltonian-independent part (the SCF energies) is compared at the 1e-8 bar
         assert np.all(np.isfinite(np.asarray(mol.NOCIEnergies)))
+
+
+def test_h2o_rhf_cartesian_d(patched, gold, tmp_path):
+    """The reference's Cartesian_L keyword through the unchanged driver."""
+    from pychem_b200 import structures as S
+    inp = str(tmp_path / "h2o.inp")
+    ref_driver.write_input(inp, "h2o", S.H2O_MONOMER, "6-31G**", extra="Cartesian_L = [2]")
+    mol = ref_driver.run(inp)
+    g = gold("h2o_631gss_cartd.npz")
+    assert mol.NOrbitals == 25
+    assert abs(mol.States[0].TotalEnergy - float(g["energy"])) < E_TOL

@@ -149,9 +149,6 @@ def test_edge_cases(eng):
 
 def test_errors_are_loud(eng):
     from pychem_b200 import _lib, structures as S
-    mol = S.Molecule([["O", 8.0, 0.0, 0.0, 0.0]], "6-31G**", cartesian_l=[2])
-    with pytest.raises(_lib.PychemB200Error):
-        eng.DeviceBasis(mol)               # Cartesian d is refused, not silently mis-computed
     db = _basis(eng, "h2")
     with pytest.raises(_lib.PychemB200Error):
         db.eri_quartets([(1, 0, 0, 0)])    # a > b
@@ -264,4 +261,40 @@ def test_other_basis_sets_vs_oracle(eng, basis, coords):
     for got in (db.jk_stored(G_dev, A + B, A, B), db.jk_direct(A + B, A, B)):
         for mine, r in zip(got, ref):
             assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
+    db.close()
+
+
+def test_cartesian_d_shells(eng, gold):
+    """Cartesian_L = [2] (Util/structures.py:844-849): six Cartesian d functions per shell; golden
+    tensor from the reference run with that keyword, plus a water dimer against the oracle."""
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    g = gold("h2o_631gss_cartd.npz")
+    mol = S.Molecule(S.H2O_MONOMER, "6-31G**", cartesian_l=[2])
+    db = eng.DeviceBasis(mol)
+    assert db.nbf == 25
+    db.schwarz()
+    G_dev, G = db.eri_tensor(1.0e-8, to_host=True)
+    assert np.abs(G - g["G"]).max() < ERI_TOL
+    db.close()
+    mol = S.Molecule(S.water_cluster(2), "6-31G**", cartesian_l=[2])
+    db = eng.DeviceBasis(mol)
+    bounds, _ = db.schwarz()
+    ob = oracle.OracleBasis(db.table)
+    assert np.abs(bounds - ob.schwarz()[0]).max() < 1e-12
+    G_dev, G = db.eri_tensor(1.0e-8, to_host=True)
+    G_ref, _ = ob.tensor(1.0e-8)
+    assert np.abs(G - G_ref).max() < ERI_TOL
+    rng = np.random.default_rng(2)
+    N = db.nbf
+    A, B = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    ref = oracle.jk(G_ref, A + B, A, B)
+    db.plan(1.0e-8, 0, 1)
+    for got in (db.jk_stored(G_dev, A + B, A, B), db.jk_direct(A + B, A, B)):
+        for mine, r in zip(got, ref):
+            assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
+    Ds = 0.5 * (A + A.T)
+    ref = oracle.jk(G_ref, 2 * Ds, Ds, Ds)
+    for mine, r in zip(db.jk_direct(2 * Ds, Ds, Ds), ref):
+        assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
     db.close()
