@@ -139,6 +139,17 @@ int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim
 int pc_launch_count(const pc_basis* h, long long* n);
 
 /*
+ * One-electron matrices (the step before the hot path): Core = kinetic energy +
+ * nuclear attraction and Overlap, N x N each (host or device), for all shell pairs in one launch.
+ *   Replaces hartree_fock.make_core_matrices' loop over integrals.one_electron
+ *   (Methods/hartree_fock.py:207-222, Methods/integrals.py:220-370) and the five
+ *   _c_ints.one_electron_* micro-step functions (Methods/_c_ints.c:400-640).
+ *   Z[natom] nuclear charges, R[natom][3] nuclear positions in bohr.
+ */
+int pc_one_electron(pc_basis* h, int natom, const double* Z, const double* R, double* core,
+                    double* overlap);
+
+/*
  * MP2: AO->MO four-index transform on the FP64 tensor cores (DMMA, mma.sync m8n8k4 f64) and the
  * UMP2 energy sums.  Replaces the O(N^6) Python loops of Methods/mp2.py:37-94 (half transforms
  * :43-69, energy sums :77-94).  G_dev: the dense tensor from pc_eri_tensor (device, N^4 doubles);

@@ -186,6 +186,22 @@ def main():
         print("LiH chain", k, mol.NOrbitals, [s.TotalEnergy for s in mol.States], mol.NOCIEnergies,
               "%.1fs" % (time.time() - t))
 
+    # ---------------- one-electron matrices (hartree_fock.make_core_matrices) ------------
+    one_e = {}
+    for name, coords, basis, extra in (("h2", [["H", 1.0, 0.0, 0.0, 0.0], ["H", 1.0, 0.0, 0.0, 1.0]], "6-311G", ""),
+                                       ("lih", [["Li", 3.0, 0.0, 0.0, 0.0], ["H", 1.0, 2.2, 0.0, 0.0]], "6-31G", ""),
+                                       ("h2o", S.H2O_MONOMER, "6-31G**", ""),
+                                       ("h2o_cartd", S.H2O_MONOMER, "6-31G**", "Cartesian_L = [2]"),
+                                       ("h2o2", S.water_cluster(2), "6-31G**", ""),
+                                       ("benzene", S.benzene(), "6-31G*", "")):
+        mol, _ = ref_driver.build_molecule(coords, basis, extra=extra)
+        with np.errstate(all="ignore"):
+            ns.hartree_fock.make_core_matrices(mol)
+        one_e[name + "_core"] = np.array(mol.Core)
+        one_e[name + "_overlap"] = np.array(mol.Overlap)
+        print("one-electron", name, mol.NOrbitals, np.trace(mol.Core), np.trace(mol.Overlap))
+    np.savez_compressed(os.path.join(GOLD, "one_electron.npz"), **one_e)
+
     # ---------------- H2O 6-31G** RHF + MP2 (reference mp2.do, O(N^6) Python) -----------
     inp = os.path.join(GOLD, "_h2o_mp2.inp")
     ref_driver.write_input(inp, "h2omp2", S.H2O_MONOMER, "6-31G**", method="MP2")

@@ -5,6 +5,7 @@
 // Reference sites are cited per function in the header.
 #include "../../include/pychem_b200.h"
 #include "pc_common.cuh"
+#include "pc_one_electron.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -320,6 +321,9 @@ struct pc_basis {
   std::vector<HostPair> pairs;  // upper-triangular order
   std::vector<Kind*> kinds;
   DevBuf<double> boys;
+  // flat shell table on the device (one-electron integrals)
+  DevBuf<int> d_l, d_K, d_poff, d_fn, d_pa, d_pb;
+  DevBuf<double> d_A, d_exps, d_scc;
   bool schwarz_done = false;
   std::vector<double> bounds;   // [npair][49]
   // plan
@@ -583,6 +587,26 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
     }
   for (Kind* k : h->kinds)
     if (upload_kind(h, k)) { delete h; return 1; }
+  {
+    std::vector<int> vl, vK, vpo, vfn, vpa, vpb;
+    std::vector<double> vA;
+    for (const Shell& sh : h->shells) {
+      vl.push_back(sh.l); vK.push_back(sh.K); vpo.push_back(sh.poff); vfn.push_back(sh.first_fn);
+      for (int c = 0; c < 3; ++c) vA.push_back(sh.A[c]);
+    }
+    for (const HostPair& p : h->pairs) { vpa.push_back(p.a); vpb.push_back(p.b); }
+    cudaError_t e2 = h->d_l.upload(vl, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_K.upload(vK, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_poff.upload(vpo, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_fn.upload(vfn, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_pa.upload(vpa, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_pb.upload(vpb, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_A.upload(vA, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_exps.upload(h->exps, h->stream);
+    if (e2 == cudaSuccess) e2 = h->d_scc.upload(h->scc, h->stream);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(h->stream);
+    if (e2 != cudaSuccess) { delete h; return fail(cudaGetErrorString(e2)); }
+  }
   std::vector<double> tab = make_boys_table();
   e = h->boys.upload(tab, h->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -1190,6 +1214,35 @@ int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, c
   }
   if (pc_jk_direct_accumulate(h, variant, Dt, Da, Db, h->acc.p)) return 1;
   return pc_jk_finalize(h, variant, h->acc.p, J, Xa, Xb);
+}
+
+int pc_one_electron(pc_basis* h, int natom, const double* Z, const double* R, double* core,
+                    double* overlap) {
+  if (!h || natom <= 0 || !Z || !R || !core || !overlap) return fail("pc_one_electron: bad arguments");
+  PC_CUDA(cudaSetDevice(h->device));
+  if (ensure_scratch(h)) return 1;
+  const size_t nn = (size_t)h->nbf * h->nbf;
+  std::vector<double> zr(4 * (size_t)natom);
+  for (int c = 0; c < natom; ++c) {
+    zr[c] = Z[c];
+    for (int k = 0; k < 3; ++k) zr[natom + 3 * c + k] = R[3 * c + k];
+  }
+  DevBuf<double> dzr;
+  PC_CUDA(dzr.upload(zr, h->stream));
+  PcShellTable S;
+  S.l = h->d_l.p; S.K = h->d_K.p; S.poff = h->d_poff.p; S.first_fn = h->d_fn.p; S.A = h->d_A.p;
+  S.exps = h->d_exps.p; S.scc = h->d_scc.p; S.pair_a = h->d_pa.p; S.pair_b = h->d_pb.p;
+  S.npair = (int)h->pairs.size(); S.cart_d = h->cart_d ? 1 : 0; S.nbf = h->nbf;
+  double* o = h->ostage.p;
+  double* dcore = is_device_ptr(core) ? core : o;
+  double* dov = is_device_ptr(overlap) ? overlap : o + nn;
+  one_electron_kernel<<<(S.npair + 63) / 64, 64, 0, h->stream>>>(S, natom, dzr.p, dzr.p + natom, h->boys.p, dcore, dov);
+  PC_CUDA(cudaGetLastError());
+  h->launches += 1;
+  if (dcore != core) { if (copy_out(h, dcore, core)) return 1; }
+  if (dov != overlap) { if (copy_out(h, dov, overlap)) return 1; }
+  PC_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int pc_fp64_peak(int device, double* tflops) {

@@ -137,6 +137,18 @@ class DeviceBasis:
         self.prim_exec = prim
         return cls, kprim, tasks, ms
 
+    # ------------------------------------------------------------------ one-electron matrices
+    def one_electron(self, charges, positions):
+        """(Core, Overlap), N x N each: kinetic + nuclear attraction, and overlap
+        (hartree_fock.py:207-222).  positions in bohr."""
+        Z = np.ascontiguousarray(charges, dtype=np.float64)
+        R = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        core = np.empty((self.nbf, self.nbf))
+        overlap = np.empty((self.nbf, self.nbf))
+        _lib.check(self.lib.pc_one_electron(self.h, len(Z), Z.ctypes.data_as(_lib.c_dp),
+                                            R.ctypes.data_as(_lib.c_dp), _ptr(core), _ptr(overlap)))
+        return core, overlap
+
     # ------------------------------------------------------------------ ERIs
     def eri_quartets(self, quartets):
         """Blocks (nfa,nfb,nfc,nfd) for shell quartets [(a,b,c,d)], a<=b, c<=d."""

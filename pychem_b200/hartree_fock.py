@@ -110,19 +110,44 @@ def make_coulomb_exchange_matrices(molecule, this):
     this.Beta.Exchange = Xb
 
 
-def install(reference_hartree_fock, reference_noci=None):
+def make_core_matrices(molecule):
+    """molecule.Core / Overlap from the device (one launch for all shell pairs), then the same
+    canonical-orthogonalisation data the reference derives from the overlap matrix
+    (hartree_fock.py:207-237): X, Xt (eigenvalues above Data/constants.linear_dependence = 1e-6)
+    and the half-overlap matrix S."""
+    from .integrals import one_electron_matrices
+    core, overlap = one_electron_matrices(molecule)
+    molecule.Core = np.array(core)
+    molecule.Overlap = np.array(overlap)
+    evals, evecs = np.linalg.eigh(molecule.Overlap)
+    order = evals.argsort()[::-1]
+    evals, evecs = evals[order], evecs[:, order]
+    keep = evals > 1.0e-6
+    U = evecs[:, keep]
+    inv_root = evals[keep] ** -0.5
+    molecule.X = U * inv_root
+    molecule.Xt = molecule.X.T
+    molecule.S = (U * (1.0 / inv_root)).dot(U.T)
+
+
+def install(reference_hartree_fock, reference_noci=None, one_electron=False):
     """Rebind the two hot functions inside the reference's own modules (the drop-in).
 
     ``reference_hartree_fock`` is the reference's ``Methods.hartree_fock`` module;
     noci.py calls ``hf.make_coulomb_exchange_matrices`` through that module object, so
-    rebinding there covers NOCI as well.  Returns a callable that undoes the patch."""
+    rebinding there covers NOCI as well.  With ``one_electron=True`` make_core_matrices
+    (hartree_fock.py:207-237) is rebound too.  Returns a callable that undoes the patch."""
     saved = (reference_hartree_fock.evaluate_2e_ints,
              reference_hartree_fock.make_coulomb_exchange_matrices)
     reference_hartree_fock.evaluate_2e_ints = evaluate_2e_ints
     reference_hartree_fock.make_coulomb_exchange_matrices = make_coulomb_exchange_matrices
+    saved_core = reference_hartree_fock.make_core_matrices
+    if one_electron:
+        reference_hartree_fock.make_core_matrices = make_core_matrices
 
     def uninstall():
         reference_hartree_fock.evaluate_2e_ints, reference_hartree_fock.make_coulomb_exchange_matrices = saved
+        reference_hartree_fock.make_core_matrices = saved_core
     return uninstall
 
 

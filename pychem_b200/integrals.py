@@ -78,3 +78,27 @@ def bind(molecule):
     """Make ``molecule`` the default for two_electron()."""
     _BOUND["molecule"] = molecule
     return device_basis(molecule)
+
+
+_ONE_ELECTRON = {}
+
+
+def one_electron_matrices(molecule):
+    """(Core, Overlap) of the whole molecule from one kernel launch (cached per molecule)."""
+    db = device_basis(molecule)
+    ent = _ONE_ELECTRON.get(id(molecule))
+    if ent is None or ent[0] is not db:
+        Z = [float(a.NuclearCharge) for a in molecule.Atoms]
+        R = [[float(x) for x in a.Coordinates] for a in molecule.Atoms]
+        ent = (db,) + db.one_electron(Z, R)
+        _ONE_ELECTRON.clear()
+        _ONE_ELECTRON[id(molecule)] = ent
+    return ent[1], ent[2]
+
+
+def one_electron(molecule, shell_pair):
+    """(core, overlap) blocks of one shell pair -- same signature and return value as
+    integrals.one_electron (Methods/integrals.py:220-370)."""
+    core, overlap = one_electron_matrices(molecule)
+    ia, ib = shell_pair.Centre1.Ivec, shell_pair.Centre2.Ivec
+    return core[np.ix_(ia, ib)].copy(), overlap[np.ix_(ia, ib)].copy()
