@@ -45,6 +45,15 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
                     const int* first_fn, const double* centres /*[nshell][3] bohr*/,
                     const double* exps, const double* scc, pc_basis** out);
 int pc_basis_destroy(pc_basis* h);
+/*
+ * Integral type of the handle: 0 = electron repulsion (default), 1 = electron-scattering kernel at
+ * grid value S -- the `ints_type, grid_value` arguments of integrals.two_electron /
+ * hartree_fock.evaluate_2e_ints (Methods/_c_ints.c:236-240 -> two_electron_scattering.c,
+ * spherical_bessel_j.c; caller: Methods/properties.py:19-23).  Switching invalidates the Schwarz
+ * factors and the plan (they are recomputed from the new integrals, as the reference does).
+ * pc_schwarz, pc_plan, pc_eri_quartets and pc_eri_tensor honour it; J/K digestion is type 0 only.
+ */
+int pc_basis_set_ints_type(pc_basis* h, int ints_type, double grid_value);
 int pc_basis_nbf(const pc_basis* h, int* nbf);
 /* cudaStream_t the handle launches on (for CUDA-event timing on the launching stream). */
 int pc_basis_stream(const pc_basis* h, void** stream);

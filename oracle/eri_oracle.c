@@ -23,6 +23,8 @@
  *   Methods/hartree_fock.py:329-347                 -> orc_jk
  *   Util/structures.py:834-856, 918-956             -> shell / shell-pair constants
  *   Data/transform_basis.py:3-30                    -> cart->spherical matrices (l<=3)
+ *   Methods/c_ints/two_electron_scattering.c:6-84   -> fundamentals_scatter()  (ints_type = 1)
+ *   Methods/c_ints/spherical_bessel_j.c:5-81        -> bessel_j()
  *
  * The Boys interpolation table is missing from the reference checkout (.MISSING_LARGE_BLOBS);
  * like oracle/build_ref.py we regenerate it: cubic in sT=T/(2d) per interval of width 2d from a
@@ -253,6 +255,73 @@ static void fundamentals(double sP, double UP, const double *P, double sQ, doubl
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* scattering fundamentals (ints_type = 1): U exp(-S^2/(4 theta^2)) S^(2m) z^-m j_m(z), z = S R  */
+/* (two_electron_scattering.c:21-80, spherical_bessel_j.c:5-81)                                 */
+/* ------------------------------------------------------------------------------------------ */
+static int g_ints_type = 0;
+static double g_grid = -1.0;
+void orc_set_ints_type(int ints_type, double grid_value) { g_ints_type = ints_type; g_grid = grid_value; }
+
+static void bessel_j(double *j, double z, int l_max) {
+  const int l_thresh = 16;
+  const double half_pi = 0.5 * M_PI;
+  if (z < 1.e1) {                       /* series about z = 0 */
+    int k_max = z < 1.e-3 ? 1 : (z < 1.e-1 ? 3 : (z < 1.e0 ? 6 : 20));
+    double z2 = z * z, df = 1.0;
+    for (int m = 0; m <= l_max; m++) {
+      double mm1 = 2 * m + 1;
+      df *= mm1;
+      double jsum = 1.0, mm_df = 1.0, mm = mm1, zz = 1.0, sign = 1.0, denom = 1.0;
+      for (int k = 1; k <= k_max; k++) {
+        mm += 2; mm_df *= mm; zz *= z2; sign *= -1; denom *= 2 * k;
+        jsum += sign * zz / (denom * mm_df);
+      }
+      j[m] = jsum / df;
+    }
+  } else if (z > 1.e2) {                /* asymptotic expansion */
+    double zinv = 1 / z, zinv2 = zinv * zinv, zi = 1.0, zoff = z;
+    j[0] = sin(z) * zinv;
+    for (int m = 1; m <= l_max; m++) {
+      double mm1 = (double)(m * (m + 1) / 2);
+      zi *= zinv; zoff -= half_pi;
+      j[m] = zi * (zinv * sin(zoff) + mm1 * zinv2 * cos(zoff));
+    }
+  } else {                              /* upward recursion */
+    double jj[32];
+    double zinv = 1 / z, zinv2 = zinv * zinv;
+    jj[0] = sin(z) * zinv;
+    jj[1] = (sin(z) - z * cos(z)) * zinv2;
+    for (int m = 2; m <= l_thresh; m++) jj[m] = ((2 * m - 1) * jj[m - 1] * zinv - jj[m - 2]);
+    zinv2 = 1.0;
+    for (int m = 0; m <= l_thresh; m++) { jj[m] = jj[m] * zinv2; zinv2 *= zinv; }
+    for (int m = 0; m <= l_max; m++) j[m] = m <= l_thresh ? jj[m] : 0.0;
+  }
+  for (int m = 0; m <= l_max; m++) if (fabs(j[m]) < 1.e-16) j[m] = 0.0;
+}
+
+static void fundamentals_scatter(double sP, double UP, const double *P, double sQ, double UQ, const double *Q,
+                                 int lmax, double S, double *F, double *R) {
+  double f[ORC_MMAX + 1], S2[ORC_MMAX + 1], j[ORC_MMAX + 1];
+  double Ssq = S * S, df = 1.0, Spow = 1.0, quarter_Ssq = 0.25 * Ssq;
+  f[0] = 1.0; S2[0] = 1.0;
+  for (int m = 1; m <= lmax; m++) { Spow *= Ssq; df *= (double)(2 * m + 1); S2[m] = Spow; f[m] = 1.0 / df; }
+  double U = UP * UQ;
+  double theta_sq_inv = sP + sQ;
+  double eS = exp(-quarter_Ssq * theta_sq_inv);
+  double R2 = 0;
+  for (int i = 0; i < 3; i++) { R[i] = P[i] - Q[i]; R2 += R[i] * R[i]; }
+  if (S < 1.e-14) {
+    F[0] = U;
+    for (int m = 1; m <= lmax; m++) F[m] = 0;
+  } else if (R2 < 1.e-14) {
+    for (int m = 0; m <= lmax; m++) F[m] = U * eS * S2[m] * f[m];
+  } else {
+    bessel_j(j, S * sqrt(R2), lmax);
+    for (int m = lmax; m > -1; m--) F[m] = U * eS * S2[m] * j[m];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* VRR on one primitive quartet (two_electron_vrr.c:92-108, Gill-scaled form)                  */
 /*   V[(a_cum * NCc + c_cum) * (L+1) + m],  a_cum/c_cum = cumulative cartesian index          */
 /* ------------------------------------------------------------------------------------------ */
@@ -412,7 +481,10 @@ void orc_eri_quartet(const orc_basis *bs, int a, int b, int c, int d, double *ou
   double F[ORC_MMAX + 1], R[3];
   for (int ib = 0; ib < bra->K; ib++)
     for (int ik = 0; ik < ket->K; ik++) {
-      fundamentals(bra->sigma[ib], bra->U[ib], bra->P[ib], ket->sigma[ik], ket->U[ik], ket->P[ik], L, F, R);
+      if (g_ints_type == 1)
+        fundamentals_scatter(bra->sigma[ib], bra->U[ib], bra->P[ib], ket->sigma[ik], ket->U[ik], ket->P[ik], L, g_grid, F, R);
+      else
+        fundamentals(bra->sigma[ib], bra->U[ib], bra->P[ib], ket->sigma[ik], ket->U[ik], ket->P[ik], L, F, R);
       vrr_quartet(La, Lc, bra, ib, ket, ik, F, R, V);
       double w = bra->cc[ib] * ket->cc[ik];
       for (int e = 0; e < ne; e++)
@@ -473,7 +545,8 @@ void orc_schwarz(const orc_basis *bs, double *bounds, double *pmax) {
       size_t p = pair_index(n, a, b);
       double mx = 0;
       for (int m = 0; m < na; m++) for (int q = 0; q < nb; q++) {
-        double v = sqrt(blk[(((size_t)m * nb + q) * na + m) * nb + q]);
+        double d = blk[(((size_t)m * nb + q) * na + m) * nb + q];
+        double v = d > 0 ? sqrt(d) : 0.0;   /* scattering diagonals can dip below zero: numpy gives nan, the block is skipped either way */
         bounds[p * 49 + m * nb + q] = v;
         if (v > mx) mx = v;
       }

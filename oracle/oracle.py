@@ -36,6 +36,7 @@ def lib():
         L.orc_eri_tensor.restype = ctypes.c_long
         L.orc_eri_tensor.argtypes = [ctypes.c_void_p, ctypes.c_double, c_dp]
         L.orc_jk.argtypes = [ctypes.c_int] + [c_dp] * 7
+        L.orc_set_ints_type.argtypes = [ctypes.c_int, ctypes.c_double]
         L.orc_boys_coeff.restype = ctypes.c_double
         L.orc_boys_coeff.argtypes = [ctypes.c_int] * 3
         _LIB = L
@@ -101,3 +102,9 @@ def jk(G, Dt, Da, Db):
     J, Xa, Xb = np.zeros((N, N)), np.zeros((N, N)), np.zeros((N, N))
     lib().orc_jk(N, _dp(G), _dp(Dt), _dp(Da), _dp(Db), _dp(J), _dp(Xa), _dp(Xb))
     return J, Xa, Xb
+
+
+def set_ints_type(ints_type=0, grid_value=-1.0):
+    """0 = electron repulsion (default), 1 = scattering fundamentals at `grid_value`
+    (two_electron_scattering.c).  Global switch of the C oracle; reset it to 0 after use."""
+    lib().orc_set_ints_type(int(ints_type), float(grid_value))

@@ -16,7 +16,7 @@ REF_ROOT = os.path.join(HERE, "_ref", "pychem_py3")
 
 INPUT_TEMPLATE = """[{name}]
 Method = "{method}"
-Job_Type = "Energy"
+Job_Type = "{job_type}"
 Basis_Sets = ["{basis}"]
 Multiplicity = {mult}
 Charge = {charge}
@@ -53,22 +53,23 @@ def modules():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         import pychem
-        from Methods import hartree_fock, integrals, mp2, noci
+        from Methods import hartree_fock, integrals, mp2, noci, properties
         from Util import structures
         from Data import constants
     ns = _NS()
     ns.pychem, ns.hartree_fock, ns.integrals = pychem, hartree_fock, integrals
     ns.mp2, ns.noci, ns.structures, ns.constants = mp2, noci, structures, constants
+    ns.properties = properties
     _MODS = ns
     return ns
 
 
 def write_input(path, name, coords, basis, method="HF", reference="RHF", mult=1, charge=0,
-                maxiter=50, extra=""):
+                maxiter=50, extra="", job_type="Energy"):
     with open(path, "w") as fh:
         fh.write(INPUT_TEMPLATE.format(name=name, method=method, basis=basis, mult=mult,
                                        charge=charge, coords=repr(coords), reference=reference,
-                                       maxiter=maxiter, extra=extra))
+                                       maxiter=maxiter, extra=extra, job_type=job_type))
 
 
 def molecule_from_input(input_file):

@@ -20,6 +20,7 @@ SIGNATURES = {
     "pc_basis_create": [ctypes.c_int, ctypes.c_int, c_ip, c_ip, c_ip, c_ip, c_dp, c_dp, c_dp,
                         ctypes.POINTER(c_vp)],
     "pc_basis_destroy": [c_vp],
+    "pc_basis_set_ints_type": [c_vp, ctypes.c_int, ctypes.c_double],
     "pc_basis_nbf": [c_vp, c_ip],
     "pc_basis_stream": [c_vp, ctypes.POINTER(c_vp)],
     "pc_schwarz": [c_vp, c_dp, c_dp],

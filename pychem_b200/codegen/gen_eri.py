@@ -293,7 +293,8 @@ class ClassGen:
         s.append("      const double R0 = Px - Qx, R1 = Py - Qy, R2_ = Pz - Qz;")
         s.append("      const double Rsq = R0 * R0 + R1 * R1 + R2_ * R2_;")
         s.append("      double F[L + 1];")
-        s.append("      pc_fundamentals<L>(sP, UP, sQ, UQ, Rsq, A.boys, F);")
+        s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F);")
+        s.append("      else pc_fundamentals<L>(sP, UP, sQ, UQ, Rsq, A.boys, F);")
         s.append("      const double Rz0 = -R0 * zeta, Rz1 = -R1 * zeta, Rz2 = -R2_ * zeta;")
         s.append("      const double Re0 = R0 * eta, Re1 = R1 * eta, Re2 = R2_ * eta;")
         s.append("      const double ze = zeta * eta;")
@@ -368,7 +369,8 @@ class ClassGen:
         s.append("  const int block = %d;" % block)
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
-        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL"):
+        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
+                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT"):
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")

@@ -314,6 +314,10 @@ struct pc_basis {
   int device = 0;
   cudaStream_t stream = nullptr;
   int nshell = 0, nbf = 0;
+  int ints_type = 0;                    // 0 electron repulsion, 1 scattering (two_electron_scattering.c)
+  double grid = -1.0;                   //   ... at this grid value
+  int blocks_mode() const { return ints_type == 1 ? PC_MODE_BLOCKS_SCAT : PC_MODE_BLOCKS; }
+  int tensor_mode() const { return ints_type == 1 ? PC_MODE_TENSOR_SCAT : PC_MODE_TENSOR; }
   bool cart_d = false;                  // d shells carry their 6 Cartesians (Cartesian_L = [2])
   int nfun(int l) const { return (l == 2 && cart_d) ? 6 : 2 * l + 1; }
   std::vector<Shell> shells;
@@ -462,6 +466,7 @@ cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, c
   if (!fn) return cudaErrorInvalidValue;
   A.boys = h->boys.p;
   A.nbf = h->nbf;
+  A.scat_S = h->grid;
   cudaError_t e = fn(mode, A, st ? st : h->stream);
   if (e == cudaSuccess) h->launches += 1;
   return e;
@@ -615,6 +620,18 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
   return 0;
 }
 
+int pc_basis_set_ints_type(pc_basis* h, int ints_type, double grid_value) {
+  if (!h) return fail("pc_basis_set_ints_type: null");
+  if (ints_type != 0 && ints_type != 1) return fail("pc_basis_set_ints_type: ints_type must be 0 or 1");
+  if (h->ints_type != ints_type || (ints_type == 1 && h->grid != grid_value)) {
+    h->ints_type = ints_type;
+    h->grid = grid_value;
+    h->schwarz_done = false;       // bounds, pair order and plan belong to the integral type
+    h->planned = false;
+  }
+  return 0;
+}
+
 int pc_basis_destroy(pc_basis* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
@@ -659,7 +676,7 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax) {
       PcEriArgs A;
       memset(&A, 0, sizeof(A));
       A.out = dout.p;
-      if (launch_explicit(h, PC_MODE_BLOCKS, k, k, A, didx.p, didx.p, n)) return 1;
+      if (launch_explicit(h, h->blocks_mode(), k, k, A, didx.p, didx.p, n)) return 1;
       std::vector<double> out((size_t)nb * nb * n);
       PC_CUDA(cudaMemcpyAsync(out.data(), dout.p, out.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       PC_CUDA(cudaStreamSynchronize(h->stream));
@@ -671,7 +688,10 @@ int pc_schwarz(pc_basis* h, double* bounds, double* pmax) {
           for (int myi = 0; myi < ny; ++myi) {
             const int q = mxi * ny + myi;
             // numpy.sqrt of the diagonal (mn|mn), hartree_fock.py:251-254
-            const double v = std::sqrt(out[((size_t)q * nb + q) * n + t]);
+            // scattering diagonals can dip below zero: numpy.sqrt gives nan there and the block
+            // is skipped by the screen; 0 has the same effect
+            const double dv = out[((size_t)q * nb + q) * n + t];
+            const double v = dv > 0.0 ? std::sqrt(dv) : 0.0;
             const int ma = p.swapped ? myi : mxi, mb = p.swapped ? mxi : myi;
             h->bounds[h->pair_index(p.a, p.b) * 49 + ma * nfb + mb] = v;
             (void)nfa;
@@ -931,7 +951,7 @@ int pc_eri_quartets(pc_basis* h, int n, const int* abcd, const long long* offset
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
     A.out = dout.p;
-    if (launch_explicit(h, PC_MODE_BLOCKS, B, Kt, A, dbi.p, dkj.p, m)) return 1;
+    if (launch_explicit(h, h->blocks_mode(), B, Kt, A, dbi.p, dkj.p, m)) return 1;
     std::vector<double> res((size_t)nsph * m);
     PC_CUDA(cudaMemcpyAsync(res.data(), dout.p, res.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     PC_CUDA(cudaStreamSynchronize(h->stream));
@@ -973,7 +993,7 @@ int pc_eri_tensor(pc_basis* h, double* G_dev, double* G_host) {
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
     A.G = G_dev;
-    if (launch_group(h, PC_MODE_TENSOR, g, A, nullptr)) return 1;
+    if (launch_group(h, h->tensor_mode(), g, A, nullptr)) return 1;
   }
   if (G_host)
     PC_CUDA(cudaMemcpyAsync(G_host, G_dev, n4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1028,6 +1048,7 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
   if (variant != PC_JK_RHF && variant != PC_JK_UHF && variant != PC_JK_GEN && variant != PC_MODE_NULL)
     return fail("pc_jk_direct_accumulate: bad variant");
   if (!h->planned) return fail("pc_jk_direct_accumulate: call pc_plan first");
+  if (h->ints_type != 0) return fail("pc_jk_direct_accumulate: J/K digestion is defined for ints_type 0 only");
   if (!is_device_ptr(acc_dev)) return fail("pc_jk_direct_accumulate: acc_dev must be device memory");
   PC_CUDA(cudaSetDevice(h->device));
   if (ensure_scratch(h)) return 1;

@@ -98,6 +98,13 @@ class DeviceBasis:
         return n.value
 
     # ------------------------------------------------------------------ Schwarz + plan
+    def set_ints_type(self, ints_type=0, grid_value=-1.0):
+        """0 = electron repulsion, 1 = scattering kernel at ``grid_value`` (the ints_type /
+        grid_value arguments of integrals.two_electron, Methods/integrals.py:427).  Switching
+        drops the Schwarz factors and the plan."""
+        _lib.check(self.lib.pc_basis_set_ints_type(self.h, int(ints_type), float(grid_value)))
+        self.ints_type = int(ints_type)
+
     def schwarz(self):
         """(bounds[npair,49], pmax[npair]); hartree_fock.py:244-254."""
         bounds = np.zeros((self.npair, 49))

@@ -39,9 +39,12 @@ def _mode_for(molecule):
 
 
 def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
-    if ints_type != 0:
-        raise NotImplementedError("scattering integrals (ints_type=1) are not part of the GPU path")
+    if ints_type not in (0, 1):
+        raise ValueError("evaluate_2e_ints: ints_type must be 0 (repulsion) or 1 (scattering)")
     db = device_basis(molecule)
+    # ints_type 1: scattering kernel at grid_value (Methods/properties.py:19-23); Schwarz factors,
+    # screening and the dense tensor are then those of the scattering integrals, as in the reference
+    db.set_ints_type(ints_type, grid_value)
     table = db.table
     bounds, _ = db.schwarz()
     if not isinstance(molecule.Bounds, list) or len(molecule.Bounds) != table.nshell:
@@ -54,6 +57,11 @@ def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
             molecule.Bounds[a][b] = bounds[p, :na * nb].reshape(na, nb).copy()
             p += 1
     mode = _mode_for(molecule)
+    if ints_type == 1:
+        if 8 * int(molecule.NOrbitals) ** 4 > STORED_LIMIT_BYTES:
+            raise MemoryError("scattering integrals are consumed as a dense tensor (properties.py:22); "
+                              "N^4 exceeds PYCHEM_B200_STORED_LIMIT_GB")
+        mode = "stored"
     st = {"mode": mode, "db": db, "G_dev": None, "molecule": molecule}
     if mode == "stored":
         G_dev, G_host = db.eri_tensor(engine.INTEGRAL_THRESHOLD, to_host=True)

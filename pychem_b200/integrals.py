@@ -7,8 +7,8 @@ block being returned in (pair1 | pair2) order whichever pair carries more angula
 The whole fundamentals -> VRR -> contraction -> HRR -> normalise -> spherical chain runs in one
 CUDA kernel launch behind the C ABI (pc_eri_quartets); no CPU fallback exists.
 
-``ints_type == 1`` (scattering fundamentals, Methods/c_ints/two_electron_scattering.c) is out
-of scope of this build and raises NotImplementedError.
+``ints_type == 1`` selects the scattering fundamentals (Methods/c_ints/two_electron_scattering.c,
+spherical_bessel_j.c) at ``grid_value``; the recursion and the kernels are the same.
 """
 import numpy as np
 
@@ -58,12 +58,13 @@ def two_electron(shell_pair1, shell_pair2, ints_type=0, grid_value=-1.0, molecul
     be located in the device tables; the reference's signature has no such argument because
     its ShellPair objects carry the primitive tables themselves.
     """
-    if ints_type != 0:
-        raise NotImplementedError("scattering fundamentals (ints_type=1) are not part of the GPU path")
+    if ints_type not in (0, 1):
+        raise ValueError("two_electron: ints_type must be 0 (repulsion) or 1 (scattering)")
     molecule = molecule or _BOUND.get("molecule")
     if molecule is None:
         raise ValueError("two_electron: bind a molecule first (pychem_b200.integrals.bind)")
     db = device_basis(molecule)
+    db.set_ints_type(ints_type, grid_value)
     a = shell_index_of(molecule, shell_pair1.Centre1)
     b = shell_index_of(molecule, shell_pair1.Centre2)
     c = shell_index_of(molecule, shell_pair2.Centre1)

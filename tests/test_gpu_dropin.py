@@ -133,3 +133,33 @@ def test_h2o_rhf_cartesian_d(patched, gold, tmp_path):
     g = gold("h2o_631gss_cartd.npz")
     assert mol.NOrbitals == 25
     assert abs(mol.States[0].TotalEnergy - float(g["energy"])) < E_TOL
+
+
+def test_h2o_scattering_property_job(gold, tmp_path):
+    """The reference's property job (pychem.py:132-135 -> properties.calculate) with the CUDA
+    path installed.  Grid values where nothing is screened out (0.5, 2.0) must reproduce the
+    reference's printed intensities; at 7.5 the reference prints a history-dependent number
+    (stale tensor, see oracle/make_golden_scattering.py) and the cleared-tensor value is the bar."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, properties as prop_gpu
+    from pychem_b200 import structures as S
+    ns = ref_driver.modules()
+    undo_hf = hf_gpu.install(ns.hartree_fock)
+    undo_pr = prop_gpu.install(ns.properties)
+    try:
+        g = gold("h2o_631gss_scattering.npz")
+        inp = str(tmp_path / "h2oscat.inp")
+        ref_driver.write_input(inp, "h2oscat", S.H2O_MONOMER, "6-31G**", job_type="Property",
+                               extra='Property_Type = "Scattering"\nProperty_Grid = [0.5, 2.0, 7.5]')
+        mol = ref_driver.run(inp)
+        lines = mol.OutText.splitlines()
+        start = [i for i, l in enumerate(lines) if "Grid value -> Scattering" in l][0]
+        got = np.array([[float(x) for x in lines[start + 2 + k].split()] for k in range(3)])
+        assert abs(mol.States[0].TotalEnergy - float(g["energy"])) < E_TOL
+        assert np.abs(got[:, 1] - g["intensity"][1:]).max() < 1e-8
+        assert np.abs(got[:2, 1] - g["printed"][:2, 1]).max() < 1e-8
+        assert "End of property calculation" in mol.OutText
+    finally:
+        undo_pr()
+        undo_hf()
+        hf_gpu.release()
+        ints_gpu.release()

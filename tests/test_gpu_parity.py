@@ -298,3 +298,85 @@ def test_cartesian_d_shells(eng, gold):
     for mine, r in zip(db.jk_direct(2 * Ds, Ds, Ds), ref):
         assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
     db.close()
+
+
+# --------------------------------------------------------------------------------------------
+# scattering fundamentals (ints_type = 1): same kernels, other fundamentals
+# --------------------------------------------------------------------------------------------
+def _unpack(packed, n):
+    a, b = np.tril_indices(n)
+    p, q = np.tril_indices(len(a))
+    G = np.zeros((n,) * 4)
+    ia, ib, ic, id_ = a[p], b[p], a[q], b[q]
+    for x in ((ia, ib, ic, id_), (ib, ia, ic, id_), (ia, ib, id_, ic), (ib, ia, id_, ic),
+              (ic, id_, ia, ib), (id_, ic, ia, ib), (ic, id_, ib, ia), (id_, ic, ib, ia)):
+        G[x] = packed
+    return G
+
+
+def test_scattering_tensor_bounds_intensity_vs_reference(eng, gold):
+    """H2O 6-31G** at S = 0, 0.5, 2, 7.5 against the reference's evaluate_2e_ints(molecule, 1, S)
+    (golden: oracle/make_golden_scattering.py) and the printed intensities of properties.py."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, properties as prop_gpu
+    g = gold("h2o_631gss_scattering.npz")
+    mol = helpers.molecule("h2o")
+
+    class Spin:
+        pass
+
+    class State:
+        Total, Alpha, Beta = Spin(), Spin(), Spin()
+    State.Total.Density, State.Alpha.Density, State.Beta.Density = g["scf_Dt"], g["scf_Da"], g["scf_Db"]
+    try:
+        for k, S in enumerate(g["grid"]):
+            hf_gpu.evaluate_2e_ints(mol, 1, float(S))
+            ref = _unpack(g["G%d" % k], mol.NOrbitals)
+            assert np.abs(mol.CoulombIntegrals - ref).max() < ERI_TOL
+            refb = helpers.bounds_from_flat(ints_gpu.device_basis(mol).table, g["bounds%d" % k])
+            for (a, b), blk in refb.items():
+                assert np.abs(np.asarray(mol.Bounds[a][b]) - blk).max() < 1e-12
+            val = prop_gpu.scattering_intensity(mol, State, float(S), evaluate=False)
+            assert abs(val - g["intensity"][k]) < 1e-8
+        # back to the repulsion integrals on the same handle: Schwarz/plan are rebuilt
+        hf_gpu.evaluate_2e_ints(mol)
+        assert np.abs(mol.CoulombIntegrals - gold("h2o_631gss.npz")["G"]).max() < ERI_TOL
+    finally:
+        hf_gpu.release()
+        ints_gpu.release()
+
+
+def test_scattering_quartets_all_classes_vs_oracle(eng):
+    """Every class at a few grid values (all three regimes of the z^-m j_m(z) evaluation:
+    series z < 10, recursion, asymptotic z > 100) against the CPU oracle."""
+    from oracle import oracle
+    mol = helpers.molecule("h2o2")
+    db = eng.DeviceBasis(mol)
+    ob = oracle.OracleBasis(db.table)
+    rng = np.random.default_rng(5)
+    ns = db.table.nshell
+    quartets = []
+    for _ in range(400):
+        a, b, c, d = rng.integers(0, ns, 4)
+        quartets.append((min(a, b), max(a, b), min(c, d), max(c, d)))
+    try:
+        for S in (0.0, 1.0e-3, 0.3, 3.0, 12.0, 40.0):
+            db.set_ints_type(1, S)
+            oracle.set_ints_type(1, S)
+            blocks = db.eri_quartets(quartets)
+            worst = 0.0
+            for q, blk in zip(quartets, blocks):
+                worst = max(worst, float(np.abs(blk - ob.quartet(*[int(x) for x in q])).max()))
+            assert worst < ERI_TOL, (S, worst)
+    finally:
+        oracle.set_ints_type(0, -1.0)
+        db.close()
+
+
+def test_scattering_refuses_direct_digestion(eng):
+    db = _basis(eng, "h2")
+    db.set_ints_type(1, 0.5)
+    db.plan()
+    D = np.eye(db.nbf)
+    with pytest.raises(RuntimeError):
+        db.jk_direct(D, D, D)
+    db.close()

@@ -87,3 +87,38 @@ def test_live_reference_quartets():
         c, d = min(c, d), max(c, d)
         ref = ns.integrals.two_electron(mol.ShellPairs[(a, b)], mol.ShellPairs[(c, d)], 0, -1.0)
         assert np.abs(ob.quartet(a, b, c, d) - ref).max() < ERI_TOL
+
+
+def _unpack(packed, n):
+    """Golden scattering tensors hold one value per canonical (ab|cd), a>=b, c>=d, ab>=cd."""
+    a, b = np.tril_indices(n)
+    p, q = np.tril_indices(len(a))
+    G = np.zeros((n,) * 4)
+    ia, ib, ic, id_ = a[p], b[p], a[q], b[q]
+    for x in ((ia, ib, ic, id_), (ib, ia, ic, id_), (ia, ib, id_, ic), (ib, ia, id_, ic),
+              (ic, id_, ia, ib), (id_, ic, ia, ib), (ic, id_, ib, ia), (id_, ic, ib, ia)):
+        G[x] = packed
+    return G
+
+
+def test_scattering_integrals_match_reference(gold):
+    """ints_type = 1 (two_electron_scattering.c, spherical_bessel_j.c) at S = 0, 0.5, 2, 7.5:
+    tensor, Schwarz factors and the scattering intensity of the RHF state (properties.py:19-23)."""
+    g = gold("h2o_631gss_scattering.npz")
+    tb = BasisTable(helpers.molecule("h2o"))
+    ob = oracle.OracleBasis(tb)
+    try:
+        for k, S in enumerate(g["grid"]):
+            oracle.set_ints_type(1, float(S))
+            G, _ = ob.tensor(1.0e-8)
+            ref = _unpack(g["G%d" % k], tb.nbf)
+            assert np.abs(G - ref).max() < ERI_TOL
+            bounds, _ = ob.schwarz()
+            assert np.abs(bounds - g["bounds%d" % k]).max() < 1e-12
+            Dt, Da, Db = g["scf_Dt"], g["scf_Da"], g["scf_Db"]
+            J, Xa, Xb = oracle.jk(G, Dt, Da, Db)
+            val = 10 + (Dt * J).sum() + (Da * Xa).sum() + (Db * Xb).sum()
+            assert abs(val - g["intensity"][k]) < 1e-9
+        assert abs(g["intensity"][0] - 100.0) < 1e-9      # S = 0: N_el^2
+    finally:
+        oracle.set_ints_type(0, -1.0)
