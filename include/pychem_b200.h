@@ -175,6 +175,21 @@ const char* pc_mp2_last_error(void);
 /* C (M x N) = A (M x K) . B (K x N), row-major device buffers, through the same DMMA kernel. */
 int pc_dgemm_dmma(int device, int M, int N, int K, const double* A, const double* B, double* C);
 
+/*
+ * Test hook, pure host code (no device needed): the segment builder pc_plan applies to one
+ * (bra bucket, ket bucket) -- the loop nest and Schwarz screen of Methods/hartree_fock.py:276-295.
+ * pm_*: Schwarz maxima by position (groups of pairs sharing their primary shell, descending inside
+ * a group, groups by descending maximum), gstart_*: [groups+1] group starts.  Returns per segment
+ * seg_ij = (first bra pair | run << 24 | forced << 28, first ket pair), the exclusive prefixes
+ * seg_off [n_seg+1] (tasks = ket pairs) and seg_quartets [n_seg+1].  A task's thread keeps the bra
+ * pairs i of the run with pm_bra[i]*pm_ket[j] > thresh (and i <= j when same), or the single
+ * forced pair.
+ */
+int pc_plan_segments_host(int nb, const double* pm_bra, int nbg, const int* gstart_bra, int nk,
+                          const double* pm_ket, int nkg, const int* gstart_ket, int same, int run,
+                          double thresh, int max_seg, int* n_seg, long long* seg_off, int* seg_ij,
+                          long long* seg_quartets);
+
 /* Register-resident DFMA micro-benchmark: measured FP64 FMA peak of `device` in TFLOP/s
  * (the roofline denominator for the ERI kernels; MEASURED_PEAKS.json has no FP64 entry). */
 int pc_fp64_peak(int device, double* tflops);

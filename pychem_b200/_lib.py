@@ -37,6 +37,8 @@ SIGNATURES = {
     "pc_set_profiling": [c_vp, ctypes.c_int],
     "pc_plan_items": [c_vp, ctypes.c_int, c_ip, c_ip, c_ip, c_llp, ctypes.POINTER(ctypes.c_float), c_dp],
     "pc_one_electron": [c_vp, ctypes.c_int, c_dp, c_dp, c_vp, c_vp],
+    "pc_plan_segments_host": [ctypes.c_int, c_dp, ctypes.c_int, c_ip, ctypes.c_int, c_dp, ctypes.c_int, c_ip,
+                              ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_ip, c_llp, c_ip, c_llp],
     "pc_fp64_peak": [ctypes.c_int, c_dp],
     "pc_mp2_energy": [ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                       ctypes.c_int, c_dp, c_dp, c_dp],

@@ -149,12 +149,50 @@ class ClassGen:
 
     # ------------------------------------------------------------------ VRR
     def gen_vrr(self):
+        """Vertical recursion of one primitive quartet + accumulation into acc[].  Elements that
+        only feed the accumulation (never an operand of a higher element) take acc as the seed of
+        their FMA chain: n FMAs instead of a multiply, n-1 FMAs and an add."""
+        zero = (0, 0, 0)
+        # pass 1: which elements are operands of other elements
+        operand = set()
+        seen = set()
+
+        def walk(a, c, m, top):
+            key = (a, c, m)
+            if not top:
+                operand.add(key)
+            if key in seen:
+                return
+            seen.add(key)
+            if a == zero and c == zero:
+                return
+            if a == zero:
+                d = first_dir(c)
+                c0 = dec(c, d)
+                walk(zero, c0, m, False); walk(zero, c0, m + 1, False)
+                if c0[d] > 0:
+                    c1 = dec(c0, d)
+                    walk(zero, c1, m, False); walk(zero, c1, m + 1, False)
+            else:
+                d = first_dir(a)
+                a0 = dec(a, d)
+                walk(a0, c, m, False); walk(a0, c, m + 1, False)
+                if a0[d] > 0:
+                    a1 = dec(a0, d)
+                    walk(a1, c, m, False); walk(a1, c, m + 1, False)
+                if c[d] > 0:
+                    walk(a0, dec(c, d), m + 1, False)
+
+        for e in self.e_list:
+            for f in self.f_list:
+                walk(e, f, 0, True)
+
         em = Emit("v")
         memo = {}
-        zero = (0, 0, 0)
         self.vrr_refs = 0
 
-        def get(a, c, m):
+        def get(a, c, m, seed=None):
+            """seed: name of the accumulator the element is added to (accumulate-only elements)."""
             key = (a, c, m)
             if key in memo:
                 return memo[key]
@@ -165,19 +203,23 @@ class ClassGen:
                 c0 = dec(c, d)
                 n = c0[d]
                 b0, b1 = get(zero, c0, m), get(zero, c0, m + 1)
-                expr = "fma(QX%d, %s, Re%d * %s)" % (d, b0, d, b1)
+                tail = "Re%d * %s" % (d, b1) if seed is None else "fma(Re%d, %s, %s)" % (d, b1, seed)
+                expr = "fma(QX%d, %s, %s)" % (d, b0, tail)
                 self.vrr_refs += 2 + (2 if n > 0 else 0)
                 if n > 0:
                     c1 = dec(c0, d)
                     b2, b3 = get(zero, c1, m), get(zero, c1, m + 1)
                     expr = "fma(ne%d, fma(-eta, %s, %s), %s)" % (n, b3, b2, expr)
+                if seed is not None:
+                    return expr
                 val = em.new(expr)
             else:
                 d = first_dir(a)
                 a0 = dec(a, d)
                 n = a0[d]
                 b0, b1 = get(a0, c, m), get(a0, c, m + 1)
-                expr = "fma(PX%d, %s, Rz%d * %s)" % (d, b0, d, b1)
+                tail = "Rz%d * %s" % (d, b1) if seed is None else "fma(Rz%d, %s, %s)" % (d, b1, seed)
+                expr = "fma(PX%d, %s, %s)" % (d, b0, tail)
                 self.vrr_refs += 2 + (2 if n > 0 else 0) + (1 if c[d] > 0 else 0)
                 if n > 0:
                     a1 = dec(a0, d)
@@ -186,15 +228,22 @@ class ClassGen:
                 if c[d] > 0:
                     b4 = get(a0, dec(c, d), m + 1)
                     expr = "fma(nze%d, %s, %s)" % (c[d], b4, expr)
+                if seed is not None:
+                    return expr
                 val = em.new(expr)
             memo[key] = val
             return val
 
+        n_fused = 0
         for ie, e in enumerate(self.e_list):
             for jf, f in enumerate(self.f_list):
-                v = get(e, f, 0)
-                em.raw("acc[%d] += %s;" % (ie * self.nf + jf, v))
-        self.n_vrr = em.n
+                k = ie * self.nf + jf
+                if (e, f, 0) not in operand and not (e == zero and f == zero) and FUSE_ACC:
+                    em.raw("acc[%d] = %s;" % (k, get(e, f, 0, seed="acc[%d]" % k)))
+                    n_fused += 1
+                else:
+                    em.raw("acc[%d] += %s;" % (k, get(e, f, 0)))
+        self.n_vrr = em.n + n_fused
         return em.lines
 
     # ------------------------------------------------------------------ HRR + c2s
@@ -273,23 +322,37 @@ class ClassGen:
     V2 = False
 
     def prim_prologue(self, s, nmax):
-        """Primitive loops: ket primitives outside (per-lane, coalesced loads, once per ket
-        primitive), bra primitives inside (warp-uniform addresses -> broadcast loads)."""
+        """Primitive loops.  Default: ket primitives outside (per-lane, coalesced loads, once per
+        ket primitive), bra primitives inside (warp-uniform addresses -> broadcast loads).
+        Classes with an s-s ket (nothing to hoist on the ket side) run the bra primitives outside
+        so the bra-only factors (zeta, P-X) leave the inner loop."""
+        bra_outer = (self.Lc == 0 and self.La > 0 and not self.V2 and BRA_OUTER)
+        ket_load = ["const double2 q0 = __ldg(kp), q1 = __ldg(kp + nk), q2 = __ldg(kp + 2 * (size_t)nk);",
+                    "const double sQ = q0.x, UQ = q0.y, Qx = q1.x, Qy = q1.y, Qz = q2.x, kzQ = q2.y;",
+                    "const double eta = 0.5 * sQ;",
+                    "const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;"]
+        ket_load += ["const double ne%d = %d.0 * eta;" % (n, n) for n in range(1, nmax + 1)]
+        bra_load = ["const double2 p0 = __ldg(bq), p1 = __ldg(bq + nb), p2 = __ldg(bq + 2 * (size_t)nb);",
+                    "const double sP = p0.x, UP = p0.y, Px = p1.x, Py = p1.y, Pz = p2.x, kzP = p2.y;",
+                    "const double zeta = 0.5 * sP;",
+                    "const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;"]
+        bra_load += ["const double nz%d = %d.0 * zeta;" % (n, n) for n in range(1, nmax + 1)]
         s.append("  const double2* __restrict__ bp = reinterpret_cast<const double2*>(I.bra.prim) + i;")
-        s.append("  const double2* __restrict__ kp = reinterpret_cast<const double2*>(I.ket.prim) + j;")
-        s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
-        s.append("    const double2 q0 = __ldg(kp), q1 = __ldg(kp + nk), q2 = __ldg(kp + 2 * (size_t)nk);")
-        s.append("    const double sQ = q0.x, UQ = q0.y, Qx = q1.x, Qy = q1.y, Qz = q2.x, kzQ = q2.y;")
-        s.append("    const double eta = 0.5 * sQ;")
-        s.append("    const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;")
-        for n in range(1, nmax + 1):
-            s.append("    const double ne%d = %d.0 * eta;" % (n, n))
-        s.append("    const double2* __restrict__ bq = bp;")
-        s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
-        s.append("      const double2 p0 = __ldg(bq), p1 = __ldg(bq + nb), p2 = __ldg(bq + 2 * (size_t)nb);")
-        s.append("      const double sP = p0.x, UP = p0.y, Px = p1.x, Py = p1.y, Pz = p2.x, kzP = p2.y;")
-        s.append("      const double zeta = 0.5 * sP;")
-        s.append("      const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;")
+        s.append("  const double2* __restrict__ kp0 = reinterpret_cast<const double2*>(I.ket.prim) + j;")
+        if bra_outer:
+            s.append("  const double2* __restrict__ bq = bp;")
+            s.append("  for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
+            s.extend("    " + l for l in bra_load)
+            s.append("    const double2* __restrict__ kp = kp0;")
+            s.append("    for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
+            s.extend("      " + l for l in ket_load)
+        else:
+            s.append("  const double2* __restrict__ kp = kp0;")
+            s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
+            s.extend("    " + l for l in ket_load)
+            s.append("    const double2* __restrict__ bq = bp;")
+            s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
+            s.extend("      " + l for l in bra_load)
         s.append("      const double R0 = Px - Qx, R1 = Py - Qy, R2_ = Pz - Qz;")
         s.append("      const double Rsq = R0 * R0 + R1 * R1 + R2_ * R2_;")
         s.append("      double F[L + 1];")
@@ -299,7 +362,7 @@ class ClassGen:
         s.append("      const double Re0 = R0 * eta, Re1 = R1 * eta, Re2 = R2_ * eta;")
         s.append("      const double ze = zeta * eta;")
         for n in range(1, nmax + 1):
-            s.append("      const double nz%d = %d.0 * zeta; const double nze%d = %d.0 * ze;" % (n, n, n, n))
+            s.append("      const double nze%d = %d.0 * ze;" % (n, n))
         s.append("      (void)QX0; (void)QX1; (void)QX2; (void)PX0; (void)PX1; (void)PX2; (void)ze;")
         s.append("      (void)Rz0; (void)Rz1; (void)Rz2; (void)Re0; (void)Re1; (void)Re2;")
 
@@ -314,7 +377,133 @@ class ClassGen:
             return int(override)
         return {0: 8, 1: 8, 2: 6, 3: 4}.get(self.L, 1)   # tuned on (H2O)32, profiles/README.md
 
+    run = 1          # longest bra run one thread walks (1: one quartet per thread)
+
     def source(self):
+        if self.run > 1:
+            return self.source_run()
+        return self.source_single()
+
+    def launcher(self, block):
+        s = []
+        s.append("cudaError_t pc_launch_%s(int mode, const PcEriArgs& A, cudaStream_t st) {" % self.name)
+        s.append("  if (A.nwarps <= 0) return cudaSuccess;")
+        s.append("  const int block = %d;" % block)
+        s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
+        s.append("  switch (mode) {")
+        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
+                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT"):
+            s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
+        s.append("    default: return cudaErrorInvalidValue;")
+        s.append("  }")
+        s.append("  return cudaGetLastError();")
+        s.append("}")
+        return s
+
+    def run_min_blocks(self):
+        override = os.environ.get("PC_GEN_RUN_MINB_L%d" % self.L)
+        if override:
+            return int(override)
+        return {0: 8, 1: 6, 2: 5, 3: 4}.get(self.L, 3)
+
+    def source_run(self):
+        """Run form: one thread = one ket pair x a run of bra pairs sharing their primary shell
+        (pc_plan).  The generation body is the same straight-line code, inside a warp-uniform loop
+        over the run; symmetric-density digestion keeps the images without b in registers."""
+        assert not self.V2
+        lx1, ly1, lx2, ly2 = self.l
+        vrr = self.gen_vrr()
+        tail = self.gen_tail()
+        NA, NB, NC, ND = self.nsph
+        nsp = NA * NB * NC * ND
+        nmax = max(self.La, self.Lc, 1)
+        block = self.block_size()
+        dims = "%d, %d, %d, %d" % (NA, NB, NC, ND)
+        s = []
+        s.append("// GENERATED by pychem_b200/codegen/gen_eri.py -- do not edit.")
+        s.append("// class (%s%s|%s%s) [run form, up to %d bra pairs per thread]: L=%d, %d x %d contracted (e0|f0), %d VRR temporaries, %d tail temporaries"
+                 % (LNAME[lx1], LNAME[ly1], LNAME[lx2], LNAME[ly2], self.run, self.L, self.ne, self.nf, self.n_vrr, self.n_tail))
+        s.append('#include "../pc_common.cuh"')
+        s.append("")
+        s.append("namespace {")
+        s.append("constexpr int L = %d, NE = %d, NF = %d, NSPH = %d;" % (self.L, self.ne, self.nf, nsp))
+        s.extend(self.tables())
+        s.append("")
+        s.append("template <int MODE>")
+        s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const __grid_constant__ PcEriArgs A) {" % (block, self.run_min_blocks(), self.name))
+        s.append("  constexpr bool JK = (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN);")
+        s.append("  constexpr bool JKP = (MODE == PC_MODE_JK_RHF || MODE == PC_MODE_JK_UHF);   // resident images")
+        s.append("  const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);")
+        s.append("  if (gw >= A.nwarps) return;")
+        s.append("  const PcItem& I = A.items[pc_find_item(A, gw)];")
+        s.append("  const long long t = (long long)(gw - I.warp0) * 32 + (threadIdx.x & 31);")
+        s.append("  int i0, rseg, j, seg_lo, seg_hi;")
+        s.append("  bool forced;")
+        s.append("  if (!pc_decode_run(A, I, t, i0, rseg, forced, j, seg_lo, seg_hi)) return;")
+        s.append("  const int nb = I.bra.n, nk = I.ket.n, KK = __ldg(I.ket.keff + j);")
+        s.append("  const double pk = forced ? 0.0 : __ldg(I.ket.pm + j);")
+        s.append("  const double CD0 = __ldg(I.ket.xy + j), CD1 = __ldg(I.ket.xy + nk + j), CD2 = __ldg(I.ket.xy + 2 * nk + j);")
+        s.append("  int fa0 = 0, fc = 0, fd = 0;")
+        s.append("  if (JK) { fa0 = __ldg(I.bra.fx + i0); fc = __ldg(I.ket.fx + j); fd = __ldg(I.ket.fy + j); }")
+        s.append("  const int kpid = JK ? __ldg(I.ket.pid + j) : 0;")
+        s.append("  const int rmax = __reduce_max_sync(0xffffffffu, rseg);")
+        s.append("  PcRunAcc<JKP ? MODE : PC_MODE_JK_RHF, %s> RA;" % dims)
+        s.append("  if (JKP) pc_run_init(A, RA, fa0, fc, fd);")
+        s.append("#pragma unroll 1")
+        s.append("  for (int r = 0; r < rmax; ++r) {")
+        s.append("  const int i = min(i0 + r, nb - 1);")
+        s.append("  const bool live = r < rseg;")
+        s.append("  bool active = live;")
+        s.append("  if (active && !forced) active = (__ldg(I.bra.pm + i) * pk > A.thresh) && (!I.same || i <= j);")
+        s.append("  int fb = 0;")
+        s.append("  if (JK) { fb = __ldg(I.bra.fy + i); pc_run_prefetch<%s>(A, fa0, fb, fc, fd); }" % dims)
+        s.append("  double g[NSPH];")
+        s.append("  if (active) {")
+        s.append("  const int KB = __ldg(I.bra.keff + i);")
+        s.append("  const double AB0 = __ldg(I.bra.xy + i), AB1 = __ldg(I.bra.xy + nb + i), AB2 = __ldg(I.bra.xy + 2 * nb + i);")
+        s.append("  double acc[NE * NF];")
+        s.append("#pragma unroll")
+        s.append("  for (int k = 0; k < NE * NF; ++k) acc[k] = 0.0;")
+        self.prim_prologue(s, nmax)
+        for line in vrr:
+            s.append("      " + line)
+        s.append("    }")
+        s.append("  }")
+        s.append("  (void)AB0; (void)AB1; (void)AB2;")
+        for line in tail:
+            s.append("  " + line)
+        s.append("  if (!JK) pc_epilogue<MODE, %s>(A, I, t, i, j, seg_lo, seg_hi, g);" % dims)
+        s.append("  } else if (JK) {")
+        s.append("#pragma unroll")
+        s.append("    for (int k = 0; k < NSPH; ++k) g[k] = 0.0;")
+        s.append("  }")
+        s.append("  if (JK) {")
+        s.append("    // shell-level degeneracy: 1/2 per a==b, c==d, (ab)==(cd)")
+        s.append("    double fac = 1.0;")
+        s.append("    if (fa0 == fb) fac *= 0.5;")
+        s.append("    if (fc == fd) fac *= 0.5;")
+        s.append("    if (__ldg(I.bra.pid + i) == kpid) fac *= 0.5;")
+        s.append("    if (JKP) {")
+        s.append("      if (fac != 1.0) {")
+        s.append("#pragma unroll")
+        s.append("        for (int k = 0; k < NSPH; ++k) g[k] *= fac;")
+        s.append("      }")
+        s.append("      pc_run_iter(A, RA, fa0, fb, fc, fd, g, active, live, seg_lo, seg_hi);")
+        s.append("    } else {")
+        s.append("      // general densities: all images per quartet (lanes without a quartet add zeros)")
+        s.append("      pc_digest_jk<MODE, %s>(A, fa0, fb, fc, fd, fac, g, true, seg_lo, seg_hi);" % dims)
+        s.append("    }")
+        s.append("  }")
+        s.append("  }")
+        s.append("  (void)CD0; (void)CD1; (void)CD2;")
+        s.append("  if (JKP) pc_run_final(A, RA, fa0, fc, fd, rseg > 0, seg_lo, seg_hi);")
+        s.append("}")
+        s.append("}  // namespace")
+        s.append("")
+        s.extend(self.launcher(block))
+        return "\n".join(s) + "\n"
+
+    def source_single(self):
         lx1, ly1, lx2, ly2 = self.l
         vrr = self.gen_vrr()
         tail = self.gen_tail()
@@ -637,7 +826,20 @@ class ClassGenV2(ClassGen):
         return lines
 
 
+# measured on (H2O)32: slower (psss 3.73 vs 3.43 ms) -- the per-lane ket loads move into the inner
+# loop and cost more L1 wavefronts than the three multiplies saved; kept as an experiment switch
+BRA_OUTER = os.environ.get("PC_GEN_BRA_OUTER", "0") != "0"
+FUSE_ACC = os.environ.get("PC_GEN_FUSE_ACC", "1") != "0"
 V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
+
+
+# classes compiled in the run form and the longest run they take (the plan may use shorter ones,
+# PYCHEM_B200_RUN at run time); chosen where digestion is a large share of the class's time and the
+# resident images fit the register budget
+RUN_CLASSES = {"ssss": 4, "psss": 4, "psps": 4, "dsss": 4, "dsps": 4, "dspp": 4, "dsds": 4}
+if os.environ.get("PC_GEN_RUN_CLASSES") is not None:
+    RUN_CLASSES = dict((kv.split("=")[0], int(kv.split("=")[1]))
+                       for kv in os.environ["PC_GEN_RUN_CLASSES"].split(",") if kv)
 
 
 def make_class(cls, cart_d=False):
@@ -645,7 +847,10 @@ def make_class(cls, cart_d=False):
     g.gen_vrr()
     if g.n_vrr > V2_THRESHOLD:
         return ClassGenV2(*cls, cart_d=cart_d)
-    return ClassGen(*cls, cart_d=cart_d)
+    g = ClassGen(*cls, cart_d=cart_d)
+    if not (cart_d and 2 in cls):
+        g.run = RUN_CLASSES.get(g.name, 1)
+    return g
 
 
 def flop_model(g):
@@ -720,6 +925,20 @@ def main(outdir):
                 row.append(str(float(model["".join(LNAME[x] for x in b + k)][key])) if ik <= ib else "0.0")
             tab.append("  {" + ", ".join(row) + "},")
         tab.append("};")
+    tab.append("int pc_run_table[2][6][6] = {")
+    for cart in (False, True):
+        tab.append(" {")
+        for ib, b in enumerate(PAIR_CLASSES):
+            row = []
+            for ik, k in enumerate(PAIR_CLASSES):
+                if ik <= ib:
+                    g = gens.get((cart, b + k)) or gens[(False, b + k)]
+                    row.append(str(g.run))
+                else:
+                    row.append("0")
+            tab.append("  {" + ", ".join(row) + "},")
+        tab.append(" },")
+    tab.append("};")
     tab.append("int pc_block_table[2][6][6] = {")
     for cart in (False, True):
         tab.append(" {")

@@ -89,12 +89,13 @@ struct Kind {
   std::vector<double> pm;       // [n] Schwarz maximum by position
   std::vector<int> keff_h;      // [n] significant primitive pairs by position
   DevBuf<int> fx, fy, pid, keff;
-  DevBuf<double> xy, prim;
+  DevBuf<double> xy, prim, pmd;
   PcPairKind view() const {
     PcPairKind v;
     v.n = (int)pairs.size();
     v.K = K;
     v.fx = fx.p; v.fy = fy.p; v.pid = pid.p; v.keff = keff.p; v.xy = xy.p; v.prim = prim.p;
+    v.pm = pmd.p;
     return v;
   }
 };
@@ -103,7 +104,8 @@ struct PlanItem {
   int kb, kk;           // bra / ket kind
   int same;
   long long total;      // all tasks of the bucket pair
-  long long begin, count;  // this rank's slice
+  long long begin, count;  // this rank's slice (tasks; cut at segment boundaries)
+  long long total_q, count_q;  // quartets of the bucket pair / of this rank's slice
   double prim_exec;        // primitive quartets actually visited by the whole bucket pair
   int nseg;
   DevBuf<long long>* seg_off;
@@ -324,7 +326,8 @@ struct pc_basis {
   std::vector<double> exps, scc;
   std::vector<HostPair> pairs;  // upper-triangular order
   std::vector<Kind*> kinds;
-  DevBuf<double> boys;
+  DevBuf<double> boys;                  // [m][j][4]  (one-electron kernel)
+  DevBuf<double> boys_l[PC_BOYS_LMAX + 1];   // per total angular momentum L: [j][m = 0..L][4] (ERI kernels)
   // flat shell table on the device (one-electron integrals)
   DevBuf<int> d_l, d_K, d_poff, d_fn, d_pa, d_pb;
   DevBuf<double> d_A, d_exps, d_scc;
@@ -396,7 +399,7 @@ int upload_kind(pc_basis* h, Kind* k) {
   // sqrt(2/pi) of two_electron_fundamentals.c:24 for the quartet.
   const double pi34 = std::pow(M_PI, -0.75);
   const double lnorm[3] = {pi34, std::sqrt(2.0) * pi34, 2.0 * pi34};
-  const double pf_half = std::pow(2.0 / M_PI, 0.25);
+  const double pf_half = std::pow(2.0 / M_PI, 0.25) * std::pow(2.0, 0.25);   // ... and the sqrt(2) of sqrt(2 theta^2)
   for (int i = 0; i < n; ++i) {
     const HostPair& p = h->pairs[k->pairs[i]];
     const Shell& X = h->shells[p.x];
@@ -450,6 +453,7 @@ int upload_kind(pc_basis* h, Kind* k) {
   PC_CUDA(k->pid.upload(pid, h->stream));
   PC_CUDA(k->xy.upload(xy, h->stream));
   PC_CUDA(k->prim.upload(prim, h->stream));
+  if ((int)k->pm.size() == n && n > 0) PC_CUDA(k->pmd.upload(k->pm, h->stream));
   PC_CUDA(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
   for (int i = 0; i < n; ++i) h->pairs[k->pairs[i]].pos = i;
   return 0;
@@ -464,9 +468,11 @@ void fill_item(PcItem& I, const Kind* kb, const Kind* kk) {
 cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, cudaStream_t st) {
   pc_launch_fn fn = pc_launch_table[h->cart_d ? 1 : 0][pcb][pck];
   if (!fn) return cudaErrorInvalidValue;
-  A.boys = h->boys.p;
+  static const int pair_l[6] = {0, 1, 2, 2, 3, 4};      // ss ps pp ds dp dd
+  A.boys = h->boys_l[pair_l[pcb] + pair_l[pck]].p;
   A.nbf = h->nbf;
   A.scat_S = h->grid;
+  A.thresh = h->thresh;
   cudaError_t e = fn(mode, A, st ? st : h->stream);
   if (e == cudaSuccess) h->launches += 1;
   return e;
@@ -497,6 +503,7 @@ int launch_group(pc_basis* h, int mode, const LaunchGroup& g, PcEriArgs& A, cuda
     fill_item(I, h->kinds[it.kb], h->kinds[it.kk]);
     I.seg_off = it.seg_off->p; I.seg_ij = (const int2*)it.seg_ij->p; I.warp_s0 = it.warp_s0->p;
     I.nseg = it.nseg; I.t_begin = it.begin; I.t_count = it.count;
+    I.same = it.same;
     I.warp0 = warp;
     warp += (int)((it.count + 31) / 32);
   }
@@ -508,6 +515,105 @@ int launch_group(pc_basis* h, int mode, const LaunchGroup& g, PcEriArgs& A, cuda
   cudaError_t e = launch_args(h, mode, g.pcb, g.pck, A, st);
   if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
   return 0;
+}
+
+// The segments of one (bra bucket, ket bucket): pure host code (also exported for the CPU tests
+// as pc_plan_segments_host).  pm: Schwarz maximum by position, gstart: group starts, keff:
+// significant primitive pairs by position.
+void build_segments_host(const std::vector<double>& pmB, const std::vector<int>& gsB, const std::vector<int>& keffB,
+                         const std::vector<double>& pmK, const std::vector<int>& gsK, const std::vector<int>& keffK,
+                         int same, int run, double thresh, std::vector<long long>& seg_off,
+                         std::vector<long long>& seg_q, std::vector<double>& seg_prim, std::vector<int>& ij) {
+  const int ng = (int)gsK.size() - 1;
+  const int nbg = (int)gsB.size() - 1;
+  // One segment = (a RUN of up to `run` consecutive bra pairs of one bra group) x (a prefix of one
+  // ket group).  The test is the reference's: max(B_ab)*max(B_cd) > thresh, strict
+  // (hartree_fock.py:293-294); unique quartets only (ket position >= bra position inside one
+  // bucket); the diagonal (ab|ab) is always kept (hartree_fock.py:244-250).  Inside a group the
+  // pairs are ordered by descending Schwarz maximum, so the kets that survive bra pair i0+1 are a
+  // prefix of those that survive i0, and for one ket the surviving bra pairs are a prefix of the
+  // run: the segment is sized by the run's first bra pair and every thread re-tests the (exactly
+  // reproducible) product for the later ones.
+  std::vector<double> pre(keffK.size() + 1, 0.0);
+  for (size_t q = 0; q < keffK.size(); ++q) pre[q + 1] = pre[q] + keffK[q];
+  seg_off.assign(1, 0);
+  seg_q.assign(1, 0);
+  seg_prim.assign(1, 0.0);
+  ij.clear();
+  auto emit = [&](int i0, int r, int forced, int j0, int len, long long nq, double nprim) {
+    ij.push_back(i0 | (r << 24) | (forced << 28));
+    ij.push_back(j0);
+    seg_off.push_back(seg_off.back() + len);
+    seg_q.push_back(seg_q.back() + nq);
+    seg_prim.push_back(seg_prim.back() + nprim);
+  };
+  int j1[PC_MAX_RUN + 1], j0[PC_MAX_RUN + 1];
+  bool diag[PC_MAX_RUN + 1];
+  run = std::max(1, std::min(run, PC_MAX_RUN));
+  for (int bg = 0; bg < nbg; ++bg)
+    for (int i0 = gsB[bg]; i0 < gsB[bg + 1]; i0 += run) {
+      const int rr = std::min(run, gsB[bg + 1] - i0);
+      for (int q = 0; q < rr; ++q) diag[q] = !same;
+      for (int g = 0; g < ng; ++g) {
+        const int gs = gsK[g], ge = gsK[g + 1];
+        if (!(pmB[i0] * pmK[gs] > thresh)) break;     // groups are ordered by their maximum
+        int r_eff = 0;
+        long long nq = 0;
+        double nprim = 0;
+        for (int q = 0; q < rr; ++q) {
+          const double pb = pmB[i0 + q];
+          j0[q] = same ? std::max(gs, i0 + q) : gs;
+          j1[q] = gs;
+          if (pb * pmK[gs] > thresh) {
+            int lo = gs, hi = (q == 0) ? ge : j1[q - 1];     // first position that fails the test
+            if (hi > lo) {
+              while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (pb * pmK[mid] > thresh) lo = mid; else hi = mid;
+              }
+              j1[q] = hi;
+            }
+          }
+          if (j1[q] <= j0[q]) break;                          // ... and so do all later bra pairs
+          r_eff = q + 1;
+          nq += j1[q] - j0[q];
+          nprim += (double)keffB[i0 + q] * (pre[j1[q]] - pre[j0[q]]);
+          if (same && i0 + q >= j0[q] && i0 + q < j1[q]) diag[q] = true;
+        }
+        if (r_eff > 0) emit(i0, r_eff, 0, j0[0], j1[0] - j0[0], nq, nprim);
+      }
+      for (int q = 0; q < rr; ++q)
+        if (!diag[q]) emit(i0 + q, 1, 1, i0 + q, 1, 1, (double)keffB[i0 + q] * keffK[i0 + q]);
+    }
+}
+
+// Longest bra run of a class: the default of its run kernel (pc_run_table; 1 = the class has the
+// one-quartet-per-thread kernel), optionally changed at run time for the run kernels:
+// PYCHEM_B200_RUN="4" (all of them) or "psss=4,ssss=8,..." (per class; classes not named keep
+// their default).
+int run_length(const pc_basis* h, int pcb, int pck) {
+  int r = pc_run_table[h->cart_d ? 1 : 0][pcb][pck];
+  if (r <= 1) return 1;                          // not a run kernel
+  const char* e = getenv("PYCHEM_B200_RUN");
+  if (e && *e) {
+    static const char* pcname[6] = {"ss", "ps", "pp", "ds", "dp", "dd"};
+    const std::string spec(e);
+    if (spec.find('=') == std::string::npos) {
+      if (atoi(e) >= 1) r = atoi(e);
+    } else {
+      const std::string key = std::string(pcname[pcb]) + pcname[pck] + "=";
+      size_t pos = 0;
+      while ((pos = spec.find(key, pos)) != std::string::npos) {
+        if (pos == 0 || spec[pos - 1] == ',') {
+          const int v = atoi(spec.c_str() + pos + key.size());
+          if (v >= 1) r = v;
+          break;
+        }
+        pos += key.size();
+      }
+    }
+  }
+  return std::max(1, std::min(r, PC_MAX_RUN));
 }
 
 // copy a host-or-device N*N matrix into device staging (returns device pointer)
@@ -614,6 +720,18 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
   }
   std::vector<double> tab = make_boys_table();
   e = h->boys.upload(tab, h->stream);
+  // The ERI kernels of one class read the orders m = 0..L of ONE interval: per-L copies with the
+  // orders of an interval adjacent ((L+1) x 32 bytes contiguous) cost one cache line per lookup
+  // instead of L+1 lines 248 KB apart.
+  for (int L = 0; L <= PC_BOYS_LMAX && e == cudaSuccess; ++L) {
+    std::vector<double> t((size_t)PC_BOYS_NPOINTS * (L + 1) * 4);
+    for (int j = 0; j < PC_BOYS_NPOINTS; ++j)
+      for (int m = 0; m <= L; ++m)
+        for (int c = 0; c < 4; ++c)
+          t[((size_t)j * (L + 1) + m) * 4 + c] = tab[((size_t)m * PC_BOYS_NPOINTS + j) * 4 + c];
+    e = h->boys_l[L].upload(t, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);     // `t` dies here
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { delete h; return fail(cudaGetErrorString(e)); }
   *out = h;
@@ -755,59 +873,29 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     h->my_quartets = h->my_eris = h->all_quartets = h->all_eris = 0;
     // ---- phase A (host threads): the segments of every (bra bucket, ket bucket) ------------
     struct Work {
-      int kb, kk, same;
-      std::vector<long long> seg_off;
+      int kb, kk, same, run;
+      std::vector<long long> seg_off, seg_q;     // prefix of tasks / of quartets per segment
       std::vector<int> ij, s0;
-      double prim_exec = 0;
+      std::vector<double> seg_prim;              // prefix of primitive quartets per segment
     };
     std::vector<Work> work;
     const int nk = (int)h->kinds.size();
+    for (const Kind* k : h->kinds)
+      if (k->pairs.size() > (size_t)PC_SEG_I_MASK) return fail("pc_plan: more than 2^24 shell pairs in one bucket");
     for (int ka = 0; ka < nk; ++ka)
       for (int kb2 = ka; kb2 < nk; ++kb2) {
         Work w;
         w.kb = ka; w.kk = kb2;
         if (h->kinds[w.kb]->pc < h->kinds[w.kk]->pc) std::swap(w.kb, w.kk);
         w.same = (w.kb == w.kk);
+        w.run = run_length(h, h->kinds[w.kb]->pc, h->kinds[w.kk]->pc);
         work.push_back(std::move(w));
       }
     auto build_segments = [&](Work& w) {
       const Kind* B = h->kinds[w.kb];
       const Kind* Kt = h->kinds[w.kk];
-      const int nb = (int)B->pairs.size();
-      const int ng = (int)Kt->gstart.size() - 1;
-      // segments: (bra pair i) x (prefix of one ket group).  The test is the reference's:
-      // max(B_ab)*max(B_cd) > thresh, strict (hartree_fock.py:293-294); unique quartets only
-      // (ket position >= bra position inside one bucket); the diagonal (ab|ab) is always kept
-      // (hartree_fock.py:244-250).
-      std::vector<double> pre(Kt->keff_h.size() + 1, 0.0);
-      for (size_t q = 0; q < Kt->keff_h.size(); ++q) pre[q + 1] = pre[q] + Kt->keff_h[q];
-      w.seg_off.assign(1, 0);
-      auto emit = [&](int i, int j0, int len) {
-        w.ij.push_back(i);
-        w.ij.push_back(j0);
-        w.seg_off.push_back(w.seg_off.back() + len);
-        w.prim_exec += (double)B->keff_h[i] * (pre[j0 + len] - pre[j0]);
-      };
-      for (int i = 0; i < nb; ++i) {
-        const double pb = B->pm[i];
-        bool diag = !w.same;
-        for (int g = 0; g < ng; ++g) {
-          const int gs = Kt->gstart[g], ge = Kt->gstart[g + 1];
-          if (!(pb * Kt->pm[gs] > thresh)) break;       // groups are ordered by their maximum
-          int lo = gs, hi = ge;                          // first position that fails the test
-          while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (pb * Kt->pm[mid] > thresh) lo = mid; else hi = mid;
-          }
-          int j0 = gs;
-          const int j1 = hi;
-          if (w.same) j0 = std::max(j0, i);
-          if (j1 <= j0) continue;
-          if (w.same && i >= j0 && i < j1) diag = true;
-          emit(i, j0, j1 - j0);
-        }
-        if (!diag) emit(i, i, 1);
-      }
+      build_segments_host(B->pm, B->gstart, B->keff_h, Kt->pm, Kt->gstart, Kt->keff_h, w.same, w.run, thresh,
+                          w.seg_off, w.seg_q, w.seg_prim, w.ij);
     };
     auto parallel_for = [&](size_t n, const std::function<void(size_t)>& fn) {
       const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -829,25 +917,47 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       it.kb = w.kb; it.kk = w.kk; it.same = w.same;
       it.total = w.seg_off.back();
       it.begin = 0; it.count = it.total;
-      it.prim_exec = w.prim_exec;
+      it.total_q = w.seg_q.back(); it.count_q = it.total_q;
+      it.prim_exec = w.seg_prim.back();
       it.nseg = (int)w.ij.size() / 2;
       it.seg_off = nullptr; it.seg_ij = nullptr; it.warp_s0 = nullptr;
       h->plan.push_back(it);
       widx.push_back((int)k);
     }
-    auto cost_total = [&](const PlanItem& it) {
+    auto quartet_cost = [&](const PlanItem& it) {
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
       const double nsph = (double)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);
-      return it.prim_exec * pc_flop_prim_table[B->pc][Kt->pc] +
-             (double)it.total * (pc_flop_cont_table[B->pc][Kt->pc] + 40.0 * nsph + 60.0);
+      return pc_flop_cont_table[B->pc][Kt->pc] + 40.0 * nsph + 60.0;
     };
-    // every bucket pair is cut into nranks equal contiguous slices: cost inside a bucket pair is
-    // uniform, so the schedule is exactly balanced; because all bucket pairs of a class share
+    auto cost_total = [&](const PlanItem& it) {
+      return it.prim_exec * pc_flop_prim_table[h->kinds[it.kb]->pc][h->kinds[it.kk]->pc] +
+             (double)it.total_q * quartet_cost(it);
+    };
+    // every bucket pair is cut into nranks contiguous slices of equal modelled cost, at segment
+    // boundaries (the cost per quartet inside a bucket pair is nearly uniform, so the static
+    // schedule is balanced to a fraction of a percent); because all bucket pairs of a class share
     // ONE fused launch, the slices of small bucket pairs cost nothing extra
-    for (PlanItem& it : h->plan) {
-      it.begin = it.total * rank / nranks;
-      it.count = it.total * (rank + 1) / nranks - it.begin;
+    for (size_t k = 0; k < h->plan.size(); ++k) {
+      PlanItem& it = h->plan[k];
+      const Work& w = work[widx[k]];
+      const double fp = pc_flop_prim_table[h->kinds[it.kb]->pc][h->kinds[it.kk]->pc], fq = quartet_cost(it);
+      auto seg_cost = [&](int sg) { return w.seg_prim[sg] * fp + (double)w.seg_q[sg] * fq; };
+      auto cut = [&](int r) {           // first segment of rank r's slice
+        if (r <= 0) return 0;
+        if (r >= nranks) return it.nseg;
+        const double target = seg_cost(it.nseg) * r / nranks;
+        int lo = 0, hi = it.nseg;     // smallest sg with seg_cost(sg) >= target
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (seg_cost(mid) < target) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int s_begin = cut(rank), s_end = cut(rank + 1);
+      it.begin = w.seg_off[s_begin];
+      it.count = w.seg_off[s_end] - it.begin;
+      it.count_q = w.seg_q[s_end] - w.seg_q[s_begin];
     }
     // ---- phase C (host threads): segment of every warp's first task ------------------------
     parallel_for(h->plan.size(), [&](size_t k) {
@@ -880,8 +990,8 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         PC_CUDA(it.warp_s0->upload(w.s0, h->stream));
       }
       const long long nsph = (long long)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);
-      h->all_quartets += it.total; h->all_eris += it.total * nsph;
-      h->my_quartets += it.count; h->my_eris += it.count * nsph;
+      h->all_quartets += it.total_q; h->all_eris += it.total_q * nsph;
+      h->my_quartets += it.count_q; h->my_eris += it.count_q * nsph;
     }
     PC_CUDA(cudaStreamSynchronize(h->stream));      // host vectors in `work` die below
     // ---- launch groups: all bucket pairs of one class -> one fused launch, longest first ----
@@ -1154,7 +1264,7 @@ int pc_plan_items(pc_basis* h, int max_items, int* n_items, int* cls, int* kprim
     const Kind* Kt = h->kinds[it.kk];
     if (cls) { cls[4 * k] = B->lx; cls[4 * k + 1] = B->ly; cls[4 * k + 2] = Kt->lx; cls[4 * k + 3] = Kt->ly; }
     if (kprim) { kprim[2 * k] = B->K; kprim[2 * k + 1] = Kt->K; }
-    if (tasks) { tasks[2 * k] = it.total; tasks[2 * k + 1] = it.count; }
+    if (tasks) { tasks[2 * k] = it.total_q; tasks[2 * k + 1] = it.count_q; }
     if (ms) ms[k] = k < (int)h->prof_ms.size() ? h->prof_ms[k] : 0.f;
     if (prim_exec) prim_exec[k] = it.prim_exec;
   }
@@ -1263,6 +1373,26 @@ int pc_one_electron(pc_basis* h, int natom, const double* Z, const double* R, do
   if (dcore != core) { if (copy_out(h, dcore, core)) return 1; }
   if (dov != overlap) { if (copy_out(h, dov, overlap)) return 1; }
   PC_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pc_plan_segments_host(int nb, const double* pm_bra, int nbg, const int* gstart_bra, int nk,
+                           const double* pm_ket, int nkg, const int* gstart_ket, int same, int run,
+                           double thresh, int max_seg, int* n_seg, long long* seg_off, int* seg_ij,
+                           long long* seg_quartets) {
+  if (nb < 0 || nk < 0 || !pm_bra || !pm_ket || !gstart_bra || !gstart_ket || !n_seg)
+    return fail("pc_plan_segments_host: bad arguments");
+  std::vector<double> pB(pm_bra, pm_bra + nb), pK(pm_ket, pm_ket + nk);
+  std::vector<int> gB(gstart_bra, gstart_bra + nbg + 1), gK(gstart_ket, gstart_ket + nkg + 1);
+  std::vector<int> kB(nb, 1), kK(nk, 1), ij;
+  std::vector<long long> off, q;
+  std::vector<double> prim;
+  build_segments_host(pB, gB, kB, pK, gK, kK, same, run, thresh, off, q, prim, ij);
+  *n_seg = (int)ij.size() / 2;
+  if (*n_seg > max_seg) return fail("pc_plan_segments_host: max_seg too small");
+  if (seg_off) std::copy(off.begin(), off.end(), seg_off);
+  if (seg_ij) std::copy(ij.begin(), ij.end(), seg_ij);
+  if (seg_quartets) std::copy(q.begin(), q.end(), seg_quartets);
   return 0;
 }
 

@@ -120,3 +120,84 @@ def test_flop_model_matches_survey_table():
     for k in ("ssss", "psss", "psps", "ppss", "ppps", "pppp"):
         assert m[k]["flop_prim"] == survey[k]
     assert m["dddd"]["vrr_refs"] == 8122 and m["dddd"]["vrr_elems"] == 2321
+
+
+# --------------------------------------------------------------------------------------------
+# plan segments with bra runs (pure host code behind pc_plan): coverage against brute force
+# --------------------------------------------------------------------------------------------
+def _random_bucket(rng, ngroups, scale):
+    """pm by position: groups ordered by descending maximum, descending inside a group."""
+    groups = []
+    for _ in range(ngroups):
+        n = int(rng.integers(1, 12))
+        v = np.sort(scale * 10.0 ** rng.uniform(-7, 0, n))[::-1]
+        if rng.random() < 0.3 and n > 2:
+            v[1] = v[0]                                   # ties
+        groups.append(v)
+    groups.sort(key=lambda v: -v[0])
+    pm = np.concatenate(groups)
+    gstart = np.concatenate([[0], np.cumsum([len(v) for v in groups])]).astype(np.int32)
+    return np.ascontiguousarray(pm), gstart
+
+
+def _segments(lib, pmB, gB, pmK, gK, same, run, thresh):
+    from pychem_b200 import _lib
+    cap = 4 * (len(pmB) + 1) * (len(gK) + 1)
+    n = ctypes.c_int()
+    off = np.zeros(cap + 1, dtype=np.int64)
+    ij = np.zeros(2 * cap, dtype=np.int32)
+    q = np.zeros(cap + 1, dtype=np.int64)
+    _lib.check(lib.pc_plan_segments_host(len(pmB), pmB.ctypes.data_as(_lib.c_dp), len(gB) - 1,
+                                         gB.ctypes.data_as(_lib.c_ip), len(pmK), pmK.ctypes.data_as(_lib.c_dp),
+                                         len(gK) - 1, gK.ctypes.data_as(_lib.c_ip), int(same), int(run),
+                                         float(thresh), cap, ctypes.byref(n), off.ctypes.data_as(_lib.c_llp),
+                                         ij.ctypes.data_as(_lib.c_ip), q.ctypes.data_as(_lib.c_llp)))
+    return n.value, off[:n.value + 1], ij[:2 * n.value].reshape(-1, 2), q[:n.value + 1]
+
+
+@pytest.mark.parametrize("run", [1, 2, 3, 8, 15])
+@pytest.mark.parametrize("same", [0, 1])
+def test_plan_segments_cover_reference_loop_nest(run, same):
+    """Every (bra pair, ket pair) the reference's loop nest evaluates (hartree_fock.py:276-295:
+    c >= a ordering inside one bucket, strict Schwarz test, diagonal always) is produced exactly
+    once by the segments + the per-thread re-test the run kernels apply."""
+    from pychem_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(100 * run + same)
+    for trial in range(40):
+        thresh = 1.0e-8
+        pmB, gB = _random_bucket(rng, int(rng.integers(1, 9)), 10.0 ** rng.uniform(-4, 1))
+        if same:
+            pmK, gK = pmB, gB
+        else:
+            pmK, gK = _random_bucket(rng, int(rng.integers(1, 9)), 10.0 ** rng.uniform(-4, 1))
+        nseg, off, ij, q = _segments(lib, pmB, gB, pmK, gK, same, run, thresh)
+        want = set()
+        for i in range(len(pmB)):
+            for j in range(i if same else 0, len(pmK)):
+                if pmB[i] * pmK[j] > thresh or (same and i == j):
+                    want.add((i, j))
+        got = []
+        bra_group = np.searchsorted(gB, np.arange(len(pmB)), side="right")
+        ket_group = np.searchsorted(gK, np.arange(len(pmK)), side="right")
+        for s in range(nseg):
+            i0, r, forced = ij[s, 0] & 0xFFFFFF, (ij[s, 0] >> 24) & 15, (ij[s, 0] >> 28) & 1
+            j0, ln = ij[s, 1], off[s + 1] - off[s]
+            assert 1 <= r <= run and ln >= 1
+            assert len(set(bra_group[i0:i0 + r])) == 1          # a run stays inside one bra group
+            assert len(set(ket_group[j0:j0 + ln])) == 1         # ... and a segment inside one ket group
+            cnt = 0
+            for j in range(j0, j0 + ln):
+                if forced:
+                    assert r == 1 and ln == 1
+                    got.append((int(i0), int(j)))
+                    cnt += 1
+                    continue
+                mine = [i for i in range(i0, i0 + r) if pmB[i] * pmK[j] > thresh and (not same or i <= j)]
+                assert mine == list(range(i0, i0 + len(mine)))  # survivors are a prefix of the run
+                assert mine, "a task without any quartet"
+                got.extend((int(i), int(j)) for i in mine)
+                cnt += len(mine)
+            assert cnt == q[s + 1] - q[s]
+        assert len(got) == len(set(got)), "a quartet was produced twice"
+        assert set(got) == want

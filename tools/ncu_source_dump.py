@@ -30,7 +30,8 @@ for nm in names:
     t, inv, full = best
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
                           "--kernel-id", "::regex:%s:%d" % (nm, inv)], capture_output=True, text=True)
-    with gzip.open("gpurun_out/src_%s.csv.gz" % nm, "wt") as fh:
+    safe = "".join(ch if ch.isalnum() else "_" for ch in nm).strip("_")
+    with gzip.open("gpurun_out/src_%s.csv.gz" % safe, "wt") as fh:
         fh.write("# %s invocation %d duration %s\n" % (full, inv, t))
         fh.write(out.stdout)
     print(nm, "invocation", inv, "duration", t, "bytes", len(out.stdout), out.stderr[-200:])
