@@ -405,12 +405,12 @@ def run_b200(args):
     achieved = all_flops / (ms_step * 1e-3) / 1e12 / world      # per-GPU TFLOP/s over the whole step
     # dominant kernel = the class kernel with the largest share of the step (per-launch CUDA-event
     # times of one profiled build).  `traffic`: DRAM bytes of its (fused) launch from the committed
-    # ncu --set full capture (profiles/r1_final_ncu_full_fused_top4.txt) -- everything is
+    # ncu --set full capture (profiles/r1b_final_ncu_full_psss.txt) -- everything is
     # L2-resident, the path is not HBM-bound.
     top_tf = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 if top[1]["ms"] else None
     roofline = {"bound": "fp64", "achieved": top_tf, "peak": peak, "unit": "TFLOP/s",
                 "frac": (top_tf / peak) if (top_tf and peak) else None,
-                "traffic": 87.2e6 if top[0] == "psss" else None,
+                "traffic": 44.9e6 if top[0] == "psss" else None,
                 "kernel": "eri_%s_kernel<JK_RHF>: one fused launch per build covering its %d bucket pairs, %.3f ms "
                           "alone, %.1f%% of the serialised per-class total"
                           % (top[0], sum(1 for c in db.plan_items()[0] if "spd"[c[0]] + "spd"[c[1]] + "spd"[c[2]] + "spd"[c[3]] == top[0]),
@@ -418,7 +418,7 @@ def run_b200(args):
                 "peak_source": "pc_fp64_peak: register-resident DFMA loop measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the fused eri_psss launch, ncu --set "
-                                  "full, profiles/r1_final_ncu_full_fused_top4.txt (pair tables, Boys table, densities "
+                                  "full, profiles/r1b_final_ncu_full_psss.txt (35.6 MB read + 9.3 MB written; pair tables, Boys table, densities "
                                   "and accumulators are L2-resident: the kernel is LSU/atomic-bound, not HBM-bound)",
                 "whole_step": {"achieved": achieved, "frac": achieved / peak if peak else None,
                                "kernels": "all %d launches of one Fock build (21 eri_*_kernel<JK_RHF> + finalize), concurrent "

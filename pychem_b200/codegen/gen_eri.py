@@ -533,7 +533,7 @@ class ClassGen:
         s.append("  // contraction depths after the primitive-pair cut-off (per shell pair)")
         s.append("  const int nb = I.bra.n, nk = I.ket.n, KB = __ldg(I.bra.keff + i), KK = __ldg(I.ket.keff + j);")
         s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
-        s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(I.bra.fx + i), __ldg(I.bra.fy + i), __ldg(I.ket.fx + j), __ldg(I.ket.fy + j));" % (NA, NB, NC, ND))
+        s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(I.bra.fx + i), __ldg(I.bra.fy + i), __ldg(I.ket.fx + j), __ldg(I.ket.fy + j), MODE != PC_MODE_JK_GEN);" % (NA, NB, NC, ND))
         s.append("  const double AB0 = __ldg(I.bra.xy + i), AB1 = __ldg(I.bra.xy + nb + i), AB2 = __ldg(I.bra.xy + 2 * nb + i);")
         s.append("  const double CD0 = __ldg(I.ket.xy + j), CD1 = __ldg(I.ket.xy + nk + j), CD2 = __ldg(I.ket.xy + 2 * nk + j);")
         s.append("  double acc[NE * NF];")
