@@ -365,7 +365,11 @@ struct pc_basis {
   cudaGraphExec_t graph_exec = nullptr;
   long long plan_id = 0;
   long long graph_launches = 0;     // kernels inside the cached graph
+#ifdef PC_HOST_EMU
+  bool use_graphs = false;          // tests/emu: the host emulation cannot replay a captured graph
+#else
   bool use_graphs = true;
+#endif
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;     // one before every plan item + one after the last
   std::vector<float> prof_ms;               // per plan item, from the last accumulate

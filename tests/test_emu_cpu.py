@@ -1,0 +1,139 @@
+"""CPU checks of the DEVICE code: the kernel sources of pychem_b200/csrc (and the generated class
+kernels) compiled for the host by tests/emu (ucontext fibers as CUDA threads, warp collectives
+as rendezvous points) and driven through the same C ABI as on the GPU.
+
+What this covers without a GPU: warp-cooperative task decode, the generated recursions of all
+classes, run kernels and segmented shuffle reductions, J/K digestion in every variant, the
+stored-tensor kernel (block barriers), multi-rank slicing, one-electron matrices, scattering
+fundamentals.  What it cannot cover: real atomics under contention, FP64 tensor cores
+(pc_mp2.cu), timing.  The `-m gpu` tests remain the parity tests proper.
+
+Emulation arithmetic differs from the GPU's in the last bits only (reciprocal-square-root seed,
+FMA contraction chosen by g++ instead of nvcc), hence the same tolerances as the GPU tests.
+"""
+import numpy as np
+import pytest
+
+from tests import helpers
+
+ERI_TOL = 1.0e-12
+JK_TOL = 1.0e-10
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.emu import emu_engine
+    emu_engine.load()
+    return emu_engine
+
+
+def _sym(rng, n):
+    X = rng.uniform(-1, 1, (n, n))
+    return 0.5 * (X + X.T)
+
+
+@pytest.mark.parametrize("name,fixture", [("h2", "h2_6311g.npz"), ("lih", "lih_631g.npz"),
+                                          ("h2o", "h2o_631gss.npz")])
+def test_emu_tensor_bounds_jk_vs_reference_golden(emu, gold, name, fixture):
+    g = gold(fixture)
+    db = emu.EmuBasis(helpers.molecule(name))
+    bounds, _ = db.schwarz()
+    assert np.abs(bounds - g["bounds"]).max() < 1e-12
+    G = db.eri_tensor(1.0e-8)
+    assert np.abs(G - g["G"]).max() < ERI_TOL
+    Dt, Da, Db = g["Dt"], g["Da"], g["Db"]
+    ref = (g["J"], g["Xa"], g["Xb"])
+    scale = max(1.0, max(np.abs(r).max() for r in ref))
+    for got in (db.jk_stored(G, Dt, Da, Db), db.jk_direct(Dt, Da, Db), db.jk_direct(Dt, Da, Db, variant=emu.GEN)):
+        for mine, r in zip(got, ref):
+            assert np.abs(mine - r).max() < JK_TOL * scale
+    db.close()
+
+
+def test_emu_sampled_quartets_all_21_classes(emu, gold):
+    g = gold("h2o2_631gss.npz")
+    db = emu.EmuBasis(helpers.molecule("h2o2"))
+    blocks = db.eri_quartets(g["quartets"])
+    worst = 0.0
+    for blk, lo, hi in zip(blocks, g["offsets"][:-1], g["offsets"][1:]):
+        worst = max(worst, float(np.abs(blk.ravel() - g["blocks"][lo:hi]).max()))
+    assert worst < ERI_TOL, worst
+    db.close()
+
+
+def test_emu_direct_variants_and_rank_partition(emu, gold):
+    """RHF / UHF / general digestion of the planned (segment-decoded) launches against the
+    reference's einsum patterns; the accumulators of 3 ranks add up to the 1-rank result."""
+    g = gold("h2o_631gss.npz")
+    G = g["G"]
+    db = emu.EmuBasis(helpers.molecule("h2o"))
+    db.plan(1.0e-8, 0, 1)
+    rng = np.random.default_rng(3)
+    Da, Db = _sym(rng, 24), _sym(rng, 24)
+    A, B = rng.uniform(-1, 1, (24, 24)), rng.uniform(-1, 1, (24, 24))
+    for a, b, variant in ((Da, Da, emu.RHF), (Da, Db, emu.UHF), (A, B, emu.GEN)):
+        ref = (np.einsum("cd,abcd->ab", a + b, G), np.einsum("cb,abcd->ad", -a, G),
+               np.einsum("cb,abcd->ad", -b, G))
+        for got in (db.jk_direct(a + b, a, b), db.jk_direct(a + b, a, b, variant=variant)):
+            for mine, r in zip(got, ref):
+                assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
+    ref = db.jk_direct(Da + Db, Da, Db, variant=emu.UHF)
+    total = np.zeros(3 * 24 * 24)
+    quartets = 0
+    for r in range(3):
+        c = db.plan(1.0e-8, r, 3)
+        quartets += c["my_quartets"]
+        total += db.jk_direct_partial(Da + Db, Da, Db, emu.UHF)
+    assert quartets == c["all_quartets"]
+    for mine, r in zip(db.jk_finalize(total, emu.UHF), ref):
+        assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
+    db.close()
+
+
+def test_emu_cartesian_d_and_edge_cases(emu, gold):
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    g = gold("h2o_631gss_cartd.npz")
+    db = emu.EmuBasis(S.Molecule(S.H2O_MONOMER, "6-31G**", cartesian_l=[2]))
+    assert db.nbf == 25
+    db.schwarz()
+    assert np.abs(db.eri_tensor(1.0e-8) - g["G"]).max() < ERI_TOL
+    db.close()
+    for coords in ([["H", 1.0, 0.0, 0.0, 0.0]],
+                   [["O", 8.0, 0.0, 0.0, 0.0], ["O", 8.0, 0.0, 0.0, 9.0]],
+                   [["H", 1.0, 0.0, 0.0, 0.0], ["H", 1.0, 0.0, 0.0, 1.0e-9]]):
+        db = emu.EmuBasis(S.Molecule(coords, "6-31G**"))
+        db.schwarz()
+        G_ref, _ = oracle.OracleBasis(db.table).tensor(1.0e-8)
+        assert np.abs(db.eri_tensor(1.0e-8) - G_ref).max() < ERI_TOL
+        db.close()
+
+
+def test_emu_one_electron_and_scattering(emu, gold):
+    from oracle import oracle
+    mol = helpers.molecule("h2o")
+    db = emu.EmuBasis(mol)
+    g = gold("one_electron.npz")
+    Z = [float(a.NuclearCharge) for a in mol.Atoms]
+    R = [[float(x) for x in a.Coordinates] for a in mol.Atoms]
+    core, overlap = db.one_electron(Z, R)
+    assert np.abs(overlap - g["h2o_overlap"]).max() < 1e-12
+    assert np.abs(core - g["h2o_core"]).max() < 1e-12 * max(1.0, np.abs(g["h2o_core"]).max())
+    ob = oracle.OracleBasis(db.table)
+    rng = np.random.default_rng(5)
+    ns = db.table.nshell
+    quartets = []
+    for _ in range(60):
+        a, b, c, d = rng.integers(0, ns, 4)
+        quartets.append((min(a, b), max(a, b), min(c, d), max(c, d)))
+    try:
+        for S in (0.0, 0.3, 12.0):
+            db.set_ints_type(1, S)
+            oracle.set_ints_type(1, S)
+            worst = 0.0
+            for q, blk in zip(quartets, db.eri_quartets(quartets)):
+                worst = max(worst, float(np.abs(blk - ob.quartet(*[int(x) for x in q])).max()))
+            assert worst < ERI_TOL, (S, worst)
+    finally:
+        oracle.set_ints_type(0, -1.0)
+        db.close()
