@@ -132,6 +132,23 @@ int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, c
 int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double* Db, int* variant);
 
 /*
+ * Batched J/K for `nset` sets of general (possibly non-symmetric) densities in ONE pass over the
+ * integrals: NOCI builds J/K for every determinant pair with its own co-density matrices
+ * (Methods/noci.py:247,275,291 -> hartree_fock.make_coulomb_exchange_matrices per pair,
+ * Methods/hartree_fock.py:329-347); in direct mode that would regenerate all ERIs per pair.
+ *   D:   nset x [Dt | Da | Db], 3*N*N doubles per set, host or device
+ *   out: nset x [J | Xa | Xb],  3*N*N doubles per set, host or device (Exchange carries the sign)
+ *   pc_jk_stored_batch: streams the stored tensor once per 4 sets.
+ *   pc_jk_direct_batch: every ERI block of this rank's slice is generated once and digested
+ *     with all sets (general variant).  _accumulate/_finalize_batch split it for multi-GPU:
+ *     acc_dev = device buffer of nset*3*N*N doubles to be summed over ranks in between.
+ */
+int pc_jk_stored_batch(pc_basis* h, const double* G_dev, int nset, const double* D, double* out);
+int pc_jk_direct_batch(pc_basis* h, int nset, const double* D, double* out);
+int pc_jk_direct_batch_accumulate(pc_basis* h, int nset, const double* D, double* acc_dev);
+int pc_jk_finalize_batch(pc_basis* h, int nset, const double* acc_dev, double* out);
+
+/*
  * Measurement hooks (bench.py): with profiling on, pc_jk_direct_accumulate brackets every kernel
  * launch (one fused launch per angular-momentum class; its time is booked on the first bucket
  * pair of the class) with CUDA events on the launching stream and synchronises at the end.  pc_plan_items reports, per item k: cls[4k..] = (lx1,ly1,lx2,ly2),

@@ -33,6 +33,10 @@ SIGNATURES = {
     "pc_jk_direct_accumulate_auto": [c_vp, c_vp, c_vp, c_vp, c_vp, c_ip],
     "pc_jk_direct": [c_vp, ctypes.c_int] + [c_vp] * 6,
     "pc_jk_classify": [c_vp, c_vp, c_vp, c_vp, c_ip],
+    "pc_jk_stored_batch": [c_vp, c_vp, ctypes.c_int, c_vp, c_vp],
+    "pc_jk_direct_batch": [c_vp, ctypes.c_int, c_vp, c_vp],
+    "pc_jk_direct_batch_accumulate": [c_vp, ctypes.c_int, c_vp, c_vp],
+    "pc_jk_finalize_batch": [c_vp, ctypes.c_int, c_vp, c_vp],
     "pc_launch_count": [c_vp, c_llp],
     "pc_set_profiling": [c_vp, ctypes.c_int],
     "pc_plan_items": [c_vp, ctypes.c_int, c_ip, c_ip, c_ip, c_llp, ctypes.POINTER(ctypes.c_float), c_dp],

@@ -392,7 +392,7 @@ class ClassGen:
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
         for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
-                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT"):
+                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT", "PC_MODE_JK_GEN_BATCH"):
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")
@@ -431,7 +431,7 @@ class ClassGen:
         s.append("")
         s.append("template <int MODE>")
         s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const __grid_constant__ PcEriArgs A) {" % (block, self.run_min_blocks(), self.name))
-        s.append("  constexpr bool JK = (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN);")
+        s.append("  constexpr bool JK = (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN) || MODE == PC_MODE_JK_GEN_BATCH;")
         s.append("  constexpr bool JKP = (MODE == PC_MODE_JK_RHF || MODE == PC_MODE_JK_UHF);   // resident images")
         s.append("  const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);")
         s.append("  if (gw >= A.nwarps) return;")
@@ -491,7 +491,7 @@ class ClassGen:
         s.append("      pc_run_iter(A, RA, fa0, fb, fc, fd, g, active, live, seg_lo, seg_hi);")
         s.append("    } else {")
         s.append("      // general densities: all images per quartet (lanes without a quartet add zeros)")
-        s.append("      pc_digest_jk<MODE, %s>(A, fa0, fb, fc, fd, fac, g, true, seg_lo, seg_hi);" % dims)
+        s.append("      pc_digest_any<MODE, %s>(A, fa0, fb, fc, fd, fac, g, true, seg_lo, seg_hi);" % dims)
         s.append("    }")
         s.append("  }")
         s.append("  }")
@@ -559,7 +559,7 @@ class ClassGen:
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
         for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
-                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT"):
+                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT", "PC_MODE_JK_GEN_BATCH"):
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")

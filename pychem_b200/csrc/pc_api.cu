@@ -278,6 +278,119 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const d
   }
 }
 
+// Batched form of jk_stored_kernel (NOCI co-density pairs, Methods/noci.py:247,275,291): the slab
+// values are loaded once and contracted with up to NS density sets, so the tensor is streamed
+// once per NS sets instead of once per set.  D: [set][Dt | Da | Db], out: [set][J | Xa | Xb],
+// both with `stride` doubles per set.
+template <int VEC, int NB, int NS>
+__global__ void __launch_bounds__(256) jk_stored_batch_kernel(int N, int ngrp, int nset, size_t stride,
+                                                              const double* __restrict__ G,
+                                                              const double* __restrict__ D,
+                                                              double* __restrict__ out) {
+  const int a = blockIdx.x / ngrp, b0 = (blockIdx.x % ngrp) * NB;
+  const int nbv = min(NB, N - b0);
+  const size_t NN = (size_t)N * N;
+  const double* __restrict__ slab = G + ((size_t)a * N + b0) * NN;
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  constexpr int RG = 8;
+  __shared__ double red[2][RG][32 * VEC + 1];
+  double jsum[NS][NB];
+#pragma unroll
+  for (int s = 0; s < NS; ++s)
+#pragma unroll
+    for (int k = 0; k < NB; ++k) jsum[s][k] = 0.0;
+  for (int d0 = 0; d0 < N; d0 += 32 * VEC) {
+    const int d = d0 + lane * VEC;
+    double xa[NS][VEC], xb[NS][VEC];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) xa[s][v] = xb[s][v] = 0.0;
+    if (d < N) {
+      for (int c = rg; c < N; c += RG) {
+        double g[NB][VEC];
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) g[k][v] = 0.0;
+          if (k < nbv) {
+            if (VEC == 2) {
+              const double2 g2 = *reinterpret_cast<const double2*>(slab + (size_t)k * NN + (size_t)c * N + d);
+              g[k][0] = g2.x; g[k][VEC - 1] = g2.y;
+            } else {
+              g[k][0] = slab[(size_t)k * NN + (size_t)c * N + d];
+            }
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+          if (s < nset) {
+            const double* __restrict__ Dt = D + (size_t)s * stride;
+            const double* __restrict__ Da = Dt + NN;
+            const double* __restrict__ Db = Dt + 2 * NN;
+            double t[VEC];
+            if (VEC == 2) {
+              const double2 t2 = __ldg(reinterpret_cast<const double2*>(Dt + (size_t)c * N + d));
+              t[0] = t2.x; t[VEC - 1] = t2.y;
+            } else {
+              t[0] = __ldg(Dt + (size_t)c * N + d);
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+              if (k < nbv) {
+                const double da = __ldg(Da + (size_t)c * N + b0 + k), db = __ldg(Db + (size_t)c * N + b0 + k);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                  jsum[s][k] = fma(t[v], g[k][v], jsum[s][k]);
+                  xa[s][v] = fma(da, g[k][v], xa[s][v]);
+                  xb[s][v] = fma(db, g[k][v], xb[s][v]);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      if (s < nset) {                                   // uniform over the block
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          red[0][rg][lane * VEC + v] = xa[s][v];
+          red[1][rg][lane * VEC + v] = xb[s][v];
+        }
+        __syncthreads();
+        const int col = threadIdx.x % (32 * VEC), which = threadIdx.x / (32 * VEC);
+        if (which < 2 && d0 + col < N) {
+          double sum = 0.0;
+#pragma unroll
+          for (int k = 0; k < RG; ++k) sum += red[which][k][col];
+          atomicAdd(out + (size_t)s * stride + (which ? 2 : 1) * NN + (size_t)a * N + d0 + col, -sum);
+        }
+        __syncthreads();
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    if (s < nset) {
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        double v = jsum[s][k];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[0][rg][k] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < nbv) {
+        double sum = 0.0;
+        for (int k = 0; k < RG; ++k) sum += red[0][k][threadIdx.x];
+        out[(size_t)s * stride + (size_t)a * N + b0 + threadIdx.x] = sum;
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // flags |= 1 if any of Dt, Da, Db is not symmetric; flags |= 2 if Da != Db (bitwise compare of
 // values, the same test the host mirror would make with numpy.array_equal)
 __global__ void classify_kernel(int N, const double* __restrict__ Dt, const double* __restrict__ Da,
@@ -344,6 +457,7 @@ struct pc_basis {
   long long my_quartets = 0, my_eris = 0, all_quartets = 0, all_eris = 0;
   // scratch
   DevBuf<double> acc, dstage, ostage;
+  DevBuf<double> bacc, bdstage, bostage;      // batched J/K (nset x 3 N^2 each)
   DevBuf<int> flags;
   long long launches = 0;
   // side streams: the (bra bucket, ket bucket) launches of one Fock build are independent
@@ -1349,6 +1463,138 @@ int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, c
   }
   if (pc_jk_direct_accumulate(h, variant, Dt, Da, Db, h->acc.p)) return 1;
   return pc_jk_finalize(h, variant, h->acc.p, J, Xa, Xb);
+}
+
+// ------------------------------------------------------------------------------------------
+// batched J/K for general density sets (the NOCI determinant pairs)
+// ------------------------------------------------------------------------------------------
+static int ensure_batch_scratch(pc_basis* h, int nset, bool acc, bool din, bool dout) {
+  const size_t need = (size_t)nset * 3 * h->nbf * h->nbf;
+  if (acc && h->bacc.n < need) PC_CUDA(h->bacc.alloc(need));
+  if (din && h->bdstage.n < need) PC_CUDA(h->bdstage.alloc(need));
+  if (dout && h->bostage.n < need) PC_CUDA(h->bostage.alloc(need));
+  return 0;
+}
+
+static int stage_in_batch(pc_basis* h, int nset, const double* D, const double** out) {
+  if (is_device_ptr(D)) {
+    *out = D;
+    return 0;
+  }
+  if (ensure_batch_scratch(h, nset, false, true, false)) return 1;
+  PC_CUDA(cudaMemcpyAsync(h->bdstage.p, D, sizeof(double) * nset * 3 * h->nbf * h->nbf, cudaMemcpyHostToDevice, h->stream));
+  *out = h->bdstage.p;
+  return 0;
+}
+
+int pc_jk_direct_batch_accumulate(pc_basis* h, int nset, const double* D, double* acc_dev) {
+  if (!h || !D || !acc_dev || nset < 1) return fail("pc_jk_direct_batch_accumulate: bad arguments");
+  if (!h->planned) return fail("pc_jk_direct_batch_accumulate: call pc_plan first");
+  if (h->ints_type != 0) return fail("pc_jk_direct_batch_accumulate: J/K digestion is defined for ints_type 0 only");
+  if (!is_device_ptr(acc_dev)) return fail("pc_jk_direct_batch_accumulate: acc_dev must be device memory");
+  PC_CUDA(cudaSetDevice(h->device));
+  const size_t nn = (size_t)h->nbf * h->nbf;
+  const double* d;
+  if (stage_in_batch(h, nset, D, &d)) return 1;
+  PC_CUDA(cudaMemsetAsync(acc_dev, 0, sizeof(double) * nset * 3 * nn, h->stream));
+  // the class launches are independent (they only meet in the atomics): spread them over side
+  // streams like pc_jk_direct_accumulate does
+  const int nside = 4;
+  const bool fan = h->groups.size() > 1;
+  if (fan) {
+    while ((int)h->side.size() < nside) {
+      cudaStream_t st;
+      PC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      h->side.push_back(st);
+      cudaEvent_t e;
+      PC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      h->ev_join.push_back(e);
+    }
+    if (!h->ev_fork) PC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PC_CUDA(cudaEventRecord(h->ev_fork, h->stream));
+    for (int s2 = 0; s2 < nside; ++s2) PC_CUDA(cudaStreamWaitEvent(h->side[s2], h->ev_fork, 0));
+  }
+  size_t idx = 0;
+  for (const LaunchGroup& g : h->groups) {
+    PcEriArgs A;
+    memset(&A, 0, sizeof(A));
+    A.Dj = d; A.Da = d + nn; A.Db = d + 2 * nn;
+    A.Jacc = acc_dev; A.Kaacc = acc_dev + nn; A.Kbacc = acc_dev + 2 * nn;
+    A.out = acc_dev;
+    A.nset = nset;
+    A.set_stride = (long long)(3 * nn);
+    if (launch_group(h, PC_MODE_JK_GEN_BATCH, g, A, fan ? h->side[idx % nside] : h->stream)) return 1;
+    ++idx;
+  }
+  if (fan) {
+    for (int s2 = 0; s2 < nside; ++s2) {
+      PC_CUDA(cudaEventRecord(h->ev_join[s2], h->side[s2]));
+      PC_CUDA(cudaStreamWaitEvent(h->stream, h->ev_join[s2], 0));
+    }
+  }
+  return 0;
+}
+
+int pc_jk_finalize_batch(pc_basis* h, int nset, const double* acc_dev, double* out) {
+  if (!h || !acc_dev || !out || nset < 1) return fail("pc_jk_finalize_batch: bad arguments");
+  PC_CUDA(cudaSetDevice(h->device));
+  const int N = h->nbf;
+  const size_t nn = (size_t)N * N;
+  double* o = out;
+  if (!is_device_ptr(out)) {
+    if (ensure_batch_scratch(h, nset, false, false, true)) return 1;
+    o = h->bostage.p;
+  }
+  const int blocks = (int)std::min<size_t>((nn + 255) / 256, 148 * 8);
+  for (int s = 0; s < nset; ++s) {
+    const double* a = acc_dev + (size_t)s * 3 * nn;
+    double* os = o + (size_t)s * 3 * nn;
+    jk_finalize_kernel<<<blocks, 256, 0, h->stream>>>(N, 1, 2, a, os, os + nn, os + 2 * nn);
+    PC_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (o != out)
+    PC_CUDA(cudaMemcpyAsync(out, o, sizeof(double) * nset * 3 * nn, cudaMemcpyDeviceToHost, h->stream));
+  PC_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int pc_jk_direct_batch(pc_basis* h, int nset, const double* D, double* out) {
+  if (!h || nset < 1) return fail("pc_jk_direct_batch: bad arguments");
+  PC_CUDA(cudaSetDevice(h->device));
+  if (ensure_batch_scratch(h, nset, true, false, false)) return 1;
+  if (pc_jk_direct_batch_accumulate(h, nset, D, h->bacc.p)) return 1;
+  return pc_jk_finalize_batch(h, nset, h->bacc.p, out);
+}
+
+int pc_jk_stored_batch(pc_basis* h, const double* G_dev, int nset, const double* D, double* out) {
+  if (!h || !G_dev || !D || !out || nset < 1) return fail("pc_jk_stored_batch: bad arguments");
+  PC_CUDA(cudaSetDevice(h->device));
+  const int N = h->nbf;
+  const size_t nn = (size_t)N * N;
+  const double* d;
+  if (stage_in_batch(h, nset, D, &d)) return 1;
+  double* o = out;
+  if (!is_device_ptr(out)) {
+    if (ensure_batch_scratch(h, nset, false, false, true)) return 1;
+    o = h->bostage.p;
+  }
+  PC_CUDA(cudaMemsetAsync(o, 0, sizeof(double) * nset * 3 * nn, h->stream));
+  constexpr int NBG = 4, NS = 4;                 // slabs per CTA, density sets per pass over the tensor
+  const int ngrp = (N + NBG - 1) / NBG;
+  for (int s0 = 0; s0 < nset; s0 += NS) {
+    const int ns = std::min(NS, nset - s0);
+    const double* ds = d + (size_t)s0 * 3 * nn;
+    double* os = o + (size_t)s0 * 3 * nn;
+    if (N % 2 == 0) jk_stored_batch_kernel<2, NBG, NS><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, ns, 3 * nn, G_dev, ds, os);
+    else jk_stored_batch_kernel<1, NBG, NS><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, ns, 3 * nn, G_dev, ds, os);
+    PC_CUDA(cudaGetLastError());
+    h->launches += 1;
+  }
+  if (o != out)
+    PC_CUDA(cudaMemcpyAsync(out, o, sizeof(double) * nset * 3 * nn, cudaMemcpyDeviceToHost, h->stream));
+  PC_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
 }
 
 int pc_one_electron(pc_basis* h, int natom, const double* Z, const double* R, double* core,

@@ -240,6 +240,53 @@ class DeviceBasis:
         return J, Xa, Xb
 
 
+    # ------------------------------------------------------------------ batched J/K (NOCI)
+    def _batch_in(self, D):
+        D = _as_f64(D)
+        N = self.nbf
+        if tuple(D.shape[1:]) != (3, N, N):
+            raise ValueError("batched densities must have shape (nset, 3, N, N): [Dt, Da, Db] per set")
+        return D, int(D.shape[0])
+
+    def _batch_out(self, like, nset):
+        import torch
+        N = self.nbf
+        if isinstance(like, np.ndarray):
+            return torch.empty((nset, 3, N, N), dtype=torch.float64, pin_memory=True).numpy()
+        return torch.empty((nset, 3, N, N), dtype=torch.float64, device=like.device)
+
+    def jk_stored_batch(self, G_dev, D):
+        """J/K for D[s] = (Dt, Da, Db), s = 0..nset-1, from the stored tensor: out[s] = (J, Xa, Xb)."""
+        D, nset = self._batch_in(D)
+        out = self._batch_out(D, nset)
+        _lib.check(self.lib.pc_jk_stored_batch(self.h, _ptr(G_dev), nset, _ptr(D), _ptr(out)))
+        return out
+
+    def jk_direct_batch(self, D, group=None):
+        """Integral-direct J/K for all sets in one pass over the ERIs (general variant).  With a
+        multi-rank plan the partial accumulators of all sets are summed with one all-reduce."""
+        D, nset = self._batch_in(D)
+        if self.counts is None:
+            self.plan()
+        out = self._batch_out(D, nset)
+        if self.counts["nranks"] == 1:
+            _lib.check(self.lib.pc_jk_direct_batch(self.h, nset, _ptr(D), _ptr(out)))
+            return out
+        import torch
+        import torch.distributed as dist
+        acc = torch.empty(nset * 3 * self.nbf * self.nbf, dtype=torch.float64, device="cuda:%d" % self.device)
+        _lib.check(self.lib.pc_jk_direct_batch_accumulate(self.h, nset, _ptr(D), _ptr(acc)))
+        ev = torch.cuda.Event()
+        ev.record(self.torch_stream())
+        torch.cuda.current_stream().wait_event(ev)
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        ev2 = torch.cuda.Event()
+        ev2.record(torch.cuda.current_stream())
+        self.torch_stream().wait_event(ev2)
+        _lib.check(self.lib.pc_jk_finalize_batch(self.h, nset, _ptr(acc), _ptr(out)))
+        return out
+
+
 def fp64_peak_tflops(device=0):
     v = ctypes.c_double()
     _lib.check(_lib.load().pc_fp64_peak(int(device), ctypes.byref(v)))

@@ -2,6 +2,8 @@
 
     evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0)      (hartree_fock.py:241-325)
     make_coulomb_exchange_matrices(molecule, this)                 (hartree_fock.py:329-347)
+    make_coulomb_exchange_matrices_batch(molecule, states)         (the same for many states at once,
+                                                                    used by pychem_b200.noci)
 
 Same names, arguments and attribute side effects, so the reference's SCF driver
 (hartree_fock.do), NOCI (noci.py:247,275,291) and MP2 (mp2.py:46) run unchanged once
@@ -116,6 +118,34 @@ def make_coulomb_exchange_matrices(molecule, this):
     this.Total.Coulomb = J
     this.Alpha.Exchange = Xa
     this.Beta.Exchange = Xb
+
+
+def make_coulomb_exchange_matrices_batch(molecule, states):
+    """make_coulomb_exchange_matrices for a LIST of state-like objects in one pass over the
+    integrals.  NOCI calls make_coulomb_exchange_matrices once per determinant
+    pair with non-symmetric co-densities (Methods/noci.py:247,275,291); in direct mode every call
+    regenerates all ERIs, in stored mode every call streams the N^4 tensor.  Here all pairs share
+    one ERI generation (direct) or one tensor pass per four pairs (stored).  Same side effects
+    per state as the single call: fresh ``Total.Coulomb``, ``Alpha.Exchange``, ``Beta.Exchange``."""
+    states = list(states)
+    if not states:
+        return
+    st = _STATE.get(id(molecule))
+    if st is None or st["molecule"] is not molecule or st["db"].h is None:
+        evaluate_2e_ints(molecule)
+        st = _STATE[id(molecule)]
+    db = st["db"]
+    N = int(molecule.NOrbitals)
+    D = np.empty((len(states), 3, N, N))
+    for k, this in enumerate(states):
+        D[k, 0] = this.Total.Density
+        D[k, 1] = this.Alpha.Density
+        D[k, 2] = this.Beta.Density
+    out = db.jk_stored_batch(st["G_dev"], D) if st["mode"] == "stored" else db.jk_direct_batch(D)
+    for k, this in enumerate(states):
+        this.Total.Coulomb = np.array(out[k, 0])
+        this.Alpha.Exchange = np.array(out[k, 1])
+        this.Beta.Exchange = np.array(out[k, 2])
 
 
 def make_core_matrices(molecule):

@@ -150,3 +150,47 @@ class EmuBasis:
         J, Xa, Xb = (np.empty((self.nbf, self.nbf)) for _ in range(3))
         self.check(self.lib.pc_jk_finalize(self.h, variant, _p(acc), _p(J), _p(Xa), _p(Xb)))
         return J, Xa, Xb
+
+    def jk_stored_batch(self, G, D):
+        D = _f64(D)
+        out = np.empty_like(D)
+        self.check(self.lib.pc_jk_stored_batch(self.h, _p(G), int(D.shape[0]), _p(D), _p(out)))
+        return out
+
+    def jk_direct_batch(self, D):
+        D = _f64(D)
+        if self.counts is None:
+            self.plan()
+        out = np.empty_like(D)
+        self.check(self.lib.pc_jk_direct_batch(self.h, int(D.shape[0]), _p(D), _p(out)))
+        return out
+
+    def jk_direct_batch_partial(self, D):
+        D = _f64(D)
+        acc = np.empty(D.size)
+        self.check(self.lib.pc_jk_direct_batch_accumulate(self.h, int(D.shape[0]), _p(D), _p(acc)))
+        return acc
+
+    def jk_finalize_batch(self, acc, nset):
+        out = np.empty((nset, 3, self.nbf, self.nbf))
+        self.check(self.lib.pc_jk_finalize_batch(self.h, nset, _p(acc), _p(out)))
+        return out
+
+
+class EmuDeviceBasis(EmuBasis):
+    """EmuBasis with the method signatures of pychem_b200.engine.DeviceBasis, so that a CPU test
+    can run the host mirrors (pychem_b200.hartree_fock / noci) end to end over the emulated
+    kernels by monkeypatching ``pychem_b200.integrals.DeviceBasis``."""
+
+    def __init__(self, molecule_or_table, device=None):
+        super().__init__(molecule_or_table)
+
+    def eri_tensor(self, thresh=1.0e-8, to_host=True):
+        G = super().eri_tensor(thresh)
+        return G, (G if to_host else None)
+
+    def jk_direct(self, Dt, Da, Db, variant=None, group=None):
+        return super().jk_direct(Dt, Da, Db, AUTO if variant is None else variant)
+
+    def jk_direct_batch(self, D, group=None):
+        return super().jk_direct_batch(D)

@@ -137,3 +137,84 @@ def test_emu_one_electron_and_scattering(emu, gold):
     finally:
         oracle.set_ints_type(0, -1.0)
         db.close()
+
+
+@pytest.mark.parametrize("name,fixture,nset", [("h2o", "h2o_631gss.npz", 5), ("lih", "lih_631g.npz", 6)])
+def test_emu_batched_jk_general_densities(emu, gold, name, fixture, nset):
+    """nset sets of non-symmetric (NOCI co-density shaped) matrices digested in one
+    pass -- direct (PC_MODE_JK_GEN_BATCH) and stored (jk_stored_batch_kernel, 4 sets per pass plus
+    a remainder pass) -- against the reference's einsum patterns on the golden tensor, against the
+    per-set calls, and additive over a 3-rank partition."""
+    g = gold(fixture)
+    G = g["G"]
+    N = G.shape[0]
+    db = emu.EmuBasis(helpers.molecule(name))
+    rng = np.random.default_rng(11)
+    D = np.empty((nset, 3, N, N))
+    for s in range(nset):
+        D[s, 1] = rng.uniform(-1, 1, (N, N))
+        D[s, 2] = rng.uniform(-1, 1, (N, N))
+        D[s, 0] = D[s, 1] + D[s, 2]
+    D[1, 1] = 0.5 * (D[1, 1] + D[1, 1].T)       # one symmetric set among the general ones
+    ref = np.empty_like(D)
+    for s in range(nset):
+        ref[s, 0] = np.einsum("cd,abcd->ab", D[s, 0], G)
+        ref[s, 1] = np.einsum("cb,abcd->ad", -D[s, 1], G)
+        ref[s, 2] = np.einsum("cb,abcd->ad", -D[s, 2], G)
+    scale = max(1.0, np.abs(ref).max())
+    G_emu = db.eri_tensor(1.0e-8)
+    stored = db.jk_stored_batch(G_emu, D)
+    assert np.abs(stored - ref).max() < JK_TOL * scale
+    db.plan(1.0e-8, 0, 1)
+    direct = db.jk_direct_batch(D)
+    assert np.abs(direct - ref).max() < JK_TOL * scale
+    for s in (0, nset - 1):
+        single = db.jk_direct(D[s, 0], D[s, 1], D[s, 2], variant=emu.GEN)
+        for k in range(3):
+            assert np.abs(direct[s, k] - single[k]).max() < 1e-12 * scale
+    total = np.zeros(D.size)
+    for r in range(3):
+        db.plan(1.0e-8, r, 3)
+        total += db.jk_direct_batch_partial(D)
+    assert np.abs(db.jk_finalize_batch(total, nset) - ref).max() < JK_TOL * scale
+    db.close()
+
+
+@pytest.mark.parametrize("mode", ["stored", "direct"])
+def test_emu_lih_sfs_noci_batched_driver(emu, gold, monkeypatch, mode):
+    """Tests/LiH_SFS_NOCI.test.inp through the reference's own driver with the hot functions
+    rebound to the mirrors AND noci.do rebound to the batched mirror (pychem_b200.noci), the
+    kernels running in the host emulation: Hartree-Fock and NOCI energies within 1e-8 Eh of the
+    reference's C path (integration_tests.py:56-66 with the tighter bar)."""
+    import os
+    from oracle import ref_driver
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref (reference copy) not built")
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, noci as noci_gpu
+    monkeypatch.setattr(ints_gpu, "DeviceBasis", emu.EmuDeviceBasis)
+    monkeypatch.setenv("PYCHEM_B200_MODE", mode)
+    ns = ref_driver.modules()
+    undo_hf = hf_gpu.install(ns.hartree_fock)
+    undo_noci = noci_gpu.install(ns.noci)
+    calls = {"single": 0, "batch": 0}
+    single, batch = hf_gpu.make_coulomb_exchange_matrices, hf_gpu.make_coulomb_exchange_matrices_batch
+
+    def count_batch(molecule, states):
+        calls["batch"] += 1
+        return batch(molecule, states)
+    monkeypatch.setattr(hf_gpu, "make_coulomb_exchange_matrices_batch", count_batch)
+    try:
+        mol = ref_driver.run(os.path.join(ref_driver.REF_ROOT, "Tests", "LiH_SFS_NOCI.test.inp"))
+        g = gold("lih_631g.npz")
+        hf = np.array([s.TotalEnergy for s in mol.States])
+        assert np.abs(hf - g["hf"]).max() < 1.0e-8
+        assert np.abs(np.asarray(mol.NOCIEnergies) - g["noci"]).max() < 1.0e-8
+        assert calls["batch"] == 1                       # all determinant pairs in one J/K pass
+        assert "NOCI output" in mol.OutText and "Hamiltonian" in mol.OutText
+        assert (mol.CoulombIntegrals is None) == (mode == "direct")
+    finally:
+        undo_noci()
+        undo_hf()
+        hf_gpu.release()
+        ints_gpu.release()
+    del single
