@@ -351,13 +351,24 @@ class ClassGen:
             s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
             s.extend("    " + l for l in ket_load)
             s.append("    const double2* __restrict__ bq = bp;")
-            s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
+            if self.ilp2():
+                s.append("    int ib = 0;")
+                s.append("    for (; ib + 1 < KB; ib += 2, bq += 6 * (size_t)nb) {")
+                s.append("@@ILP2_BODY@@")
+            else:
+                s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
             s.extend("      " + l for l in bra_load)
         s.append("      const double R0 = Px - Qx, R1 = Py - Qy, R2_ = Pz - Qz;")
         s.append("      const double Rsq = R0 * R0 + R1 * R1 + R2_ * R2_;")
         s.append("      double F[L + 1];")
-        s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F);")
-        s.append("      else pc_fundamentals<L>(sP, UP, sQ, UQ, Rsq, A.boys, F);")
+        if FUND == "2phase":
+            s.append("      PcFundState<L> fs;")
+            s.append("      if (!(MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT)) pc_fund_p1<L>(sP, UP, sQ, UQ, Rsq, A.boys, fs);")
+            s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F); "
+                     "else pc_fund_p2<L>(fs, F);")
+        else:
+            s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F); "
+                     "else %s<L>(sP, UP, sQ, UQ, Rsq, A.boys, F);" % FUND)
         s.append("      const double Rz0 = -R0 * zeta, Rz1 = -R1 * zeta, Rz2 = -R2_ * zeta;")
         s.append("      const double Re0 = R0 * eta, Re1 = R1 * eta, Re2 = R2_ * eta;")
         s.append("      const double ze = zeta * eta;")
@@ -365,6 +376,28 @@ class ClassGen:
             s.append("      const double nze%d = %d.0 * ze;" % (n, n))
         s.append("      (void)QX0; (void)QX1; (void)QX2; (void)PX0; (void)PX1; (void)PX2; (void)ze;")
         s.append("      (void)Rz0; (void)Rz1; (void)Rz2; (void)Re0; (void)Re1; (void)Re2;")
+
+    def ilp2(self):
+        bra_outer = (self.Lc == 0 and self.La > 0 and not self.V2 and BRA_OUTER)
+        return (not self.V2) and (not bra_outer) and self.L <= ILP2_MAXL
+
+    def close_prim_loops(self, s):
+        """Close the primitive loops opened by prim_prologue (after the VRR lines were appended).
+        ILP2: the statements since the marker are one inner iteration; emit them twice interleaved
+        inside the pair loop and once more for an odd last primitive."""
+        if self.ilp2():
+            k = s.index("@@ILP2_BODY@@")
+            body = s[k + 1:]
+            del s[k:]
+            s.extend(interleave2(body, "bq + 3 * (size_t)nb"))
+            s.append("    }")
+            s.append("    if (ib < KB) {")
+            s.extend(body)
+            s.append("    }")
+            s.append("  }")
+        else:
+            s.append("    }")
+            s.append("  }")
 
     def block_size(self):
         return 128 if self.L <= 4 else 64
@@ -467,8 +500,7 @@ class ClassGen:
         self.prim_prologue(s, nmax)
         for line in vrr:
             s.append("      " + line)
-        s.append("    }")
-        s.append("  }")
+        self.close_prim_loops(s)
         s.append("  (void)AB0; (void)AB1; (void)AB2;")
         for line in tail:
             s.append("  " + line)
@@ -543,8 +575,7 @@ class ClassGen:
         self.prim_prologue(s, nmax)
         for line in vrr:
             s.append("      " + line)
-        s.append("    }")
-        s.append("  }")
+        self.close_prim_loops(s)
         s.append("  (void)AB0; (void)AB1; (void)AB2; (void)CD0; (void)CD1; (void)CD2;")
         s.append("  double g[NSPH];")
         for line in tail:
@@ -829,6 +860,54 @@ class ClassGenV2(ClassGen):
 # measured on (H2O)32: slower (psss 3.73 vs 3.43 ms) -- the per-lane ket loads move into the inner
 # loop and cost more L1 wavefronts than the three multiplies saved; kept as an experiment switch
 BRA_OUTER = os.environ.get("PC_GEN_BRA_OUTER", "0") != "0"
+# ILP2 (experiment, default off): classes with L <= PC_GEN_ILP2_MAXL process TWO bra primitives per
+# inner iteration with the statements of both copies interleaved in the source (the recursion of a
+# primitive quartet is one dependent chain; two independent chains side by side give the scheduler
+# something to overlap).  Meant to be combined with PC_GEN_FUND=bf (no branches in the body).
+ILP2_MAXL = int(os.environ.get("PC_GEN_ILP2_MAXL", "-1"))
+
+
+def interleave2(body, second_ptr):
+    """body: the statements of one inner iteration reading the bra primitive at `bq`.  Returns the
+    statements of two iterations (bq and second_ptr) interleaved line by line; every name the body
+    defines gets the suffix _B in the second copy, acc[] is shared."""
+    import re
+    names = set()
+    for line in body:
+        m = re.match(r"\s*(?:const\s+)?(?:double2?|PcFundState<L>)\s+(.*);\s*$", line)
+        if not m:
+            continue
+        decl = m.group(1)
+        depth = 0
+        cur = ""
+        parts = []
+        for ch in decl:
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            if ch == "," and depth == 0:
+                parts.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        parts.append(cur)
+        for part in parts:
+            mm = re.match(r"\s*([A-Za-z_]\w*)", part)
+            if mm:
+                names.add(mm.group(1))
+    pat = re.compile(r"\b(%s)\b" % "|".join(sorted(names, key=len, reverse=True)))
+    out = []
+    for line in body:
+        out.append(line)
+        b = pat.sub(lambda m: m.group(1) + "_B", line)
+        b = re.sub(r"\bbq\b", "(%s)" % second_ptr, b)
+        out.append(b)
+    return out
+
+
+# fundamentals: "" = three-branch form (default), "bf" = branch-free select form (experiment)
+FUND = {"": "pc_fundamentals", "bf": "pc_fundamentals_bf", "2phase": "2phase"}[os.environ.get("PC_GEN_FUND", "")]
 FUSE_ACC = os.environ.get("PC_GEN_FUSE_ACC", "1") != "0"
 V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
 

@@ -21,8 +21,10 @@ _EMU = None
 def load(build=True):
     global _EMU
     if _EMU is None:
-        path = os.path.join(HERE, "libpychem_b200_emu.so")
-        if build:
+        path = os.environ.get("PYCHEM_B200_EMU_LIB") or os.path.join(HERE, "libpychem_b200_emu.so")
+        if os.environ.get("PYCHEM_B200_EMU_LIB"):
+            pass                      # a generator variant built by tools/build_variant.py --emu
+        elif build:
             from tests.emu import build_emu
             path = build_emu.build()
         lib = ctypes.CDLL(path)
