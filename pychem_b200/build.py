@@ -59,14 +59,17 @@ def build(verbose=False, jobs=None):
         gen_eri.main(GEN)
     os.makedirs(OBJ, exist_ok=True)
     deps = [os.path.join(CSRC, "pc_common.cuh")]
-    srcs = [os.path.join(CSRC, "pc_api.cu"), os.path.join(CSRC, "pc_mp2.cu")] + sorted(
+    gen_deps = deps + [os.path.join(CSRC, "pc_generic.cuh"), os.path.join(CSRC, "pc_generic_class.h")]
+    srcs = [os.path.join(CSRC, "pc_api.cu"), os.path.join(CSRC, "pc_mp2.cu"), os.path.join(CSRC, "pc_generic.cu")] + sorted(
         os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".cu"))
-    api_deps = deps + [os.path.join(HERE, "..", "include", "pychem_b200.h")]
+    api_deps = deps + [os.path.join(HERE, "..", "include", "pychem_b200.h"), os.path.join(CSRC, "pc_one_electron.cuh"),
+                       os.path.join(CSRC, "pc_generic_class.h")]
     # biggest files first so the pool stays busy
     srcs.sort(key=lambda p: -os.path.getsize(p))
     jobs = jobs or min(8, os.cpu_count() or 1)
     with ThreadPoolExecutor(jobs) as ex:
-        res = list(ex.map(lambda s: _compile(s, api_deps if (s.endswith("pc_api.cu") or s.endswith("pc_mp2.cu")) else deps, verbose), srcs))
+        res = list(ex.map(lambda s: _compile(s, api_deps if (s.endswith("pc_api.cu") or s.endswith("pc_mp2.cu")) else
+                                              (gen_deps if s.endswith("pc_generic.cu") else deps), verbose), srcs))
     objs = [o for o, _ in res]
     if any(changed for _, changed in res) or not os.path.exists(LIB):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs

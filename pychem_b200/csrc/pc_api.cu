@@ -6,6 +6,7 @@
 #include "../../include/pychem_b200.h"
 #include "pc_common.cuh"
 #include "pc_one_electron.cuh"
+#include "pc_generic_class.h"
 
 #include <algorithm>
 #include <atomic>
@@ -65,7 +66,15 @@ struct DevBuf {
 constexpr double PC_PRIM_EPS = 1.0e-24;   // primitive-pair prefactor cut-off (see upload_kind)
 
 inline int ncart(int l) { return (l + 1) * (l + 2) / 2; }
-inline int pair_class(int lx, int ly) { return lx * (lx + 1) / 2 + ly; }  // ss ps pp ds dp dd
+inline int pair_class(int lx, int ly) { return lx * (lx + 1) / 2 + ly; }  // ss ps pp ds dp dd fs fp fd ff
+constexpr int PC_NPC_GEN = 6;      // pair classes below this have generated kernels (s, p, d shells)
+constexpr int PC_NPC = 10;         // all pair classes up to (f f|
+inline void class_l(int pc, int& lx, int& ly) {
+  lx = 0;
+  while ((lx + 1) * (lx + 2) / 2 <= pc) ++lx;
+  ly = pc - lx * (lx + 1) / 2;
+}
+inline int pair_L(int pc) { int lx, ly; class_l(pc, lx, ly); return lx + ly; }
 
 struct Shell {
   int l, K, first_fn, nfn, poff;
@@ -118,6 +127,10 @@ struct LaunchGroup {
   int pcb, pck;
   std::vector<int> items;   // indices into pc_basis::plan
   double cost;
+  // classes with an f shell (pc_generic.cuh): the launch's own scratch, so that the launches of
+  // one build can run side by side
+  DevBuf<double>* scratch = nullptr;
+  int gen_threads = 0;
 };
 
 bool is_device_ptr(const void* p) {
@@ -440,7 +453,12 @@ struct pc_basis {
   std::vector<HostPair> pairs;  // upper-triangular order
   std::vector<Kind*> kinds;
   DevBuf<double> boys;                  // [m][j][4]  (one-electron kernel)
-  DevBuf<double> boys_l[PC_BOYS_LMAX + 1];   // per total angular momentum L: [j][m = 0..L][4] (ERI kernels)
+  DevBuf<double> boys_l[4 * PCG_LMAX + 1];   // per total angular momentum L: [j][m = 0..L][4] (ERI kernels)
+  int max_l = 0;                        // highest shell angular momentum of the molecule
+  bool force_generic = false;           // PYCHEM_B200_FORCE_GENERIC=1: every class takes the generic kernel (tests)
+  DevBuf<double> gen_scratch;           // scratch of the generic kernel for explicit task lists
+  std::vector<DevBuf<double>*> gen_bufs;   // ... and of the plan's launch groups
+  bool generic(int pcb, int pck) const { return force_generic || pcb >= PC_NPC_GEN || pck >= PC_NPC_GEN; }
   // flat shell table on the device (one-electron integrals)
   DevBuf<int> d_l, d_K, d_poff, d_fn, d_pa, d_pb;
   DevBuf<double> d_A, d_exps, d_scc;
@@ -497,6 +515,7 @@ struct pc_basis {
     for (auto* k : kinds) delete k;
     for (auto* b : plan_bufs) delete b;
     for (auto* b : plan_ibufs) delete b;
+    for (auto* b : gen_bufs) delete b;
     if (stream) cudaStreamDestroy(stream);
   }
   size_t pair_index(int a, int b) const { return (size_t)a * nshell - (size_t)a * (a - 1) / 2 + (b - a); }
@@ -516,7 +535,9 @@ int upload_kind(pc_basis* h, Kind* k) {
   // lives in the generated cart->spherical code); sqrt(sqrt(2/pi)) per pair gives the
   // sqrt(2/pi) of two_electron_fundamentals.c:24 for the quartet.
   const double pi34 = std::pow(M_PI, -0.75);
-  const double lnorm[3] = {pi34, std::sqrt(2.0) * pi34, 2.0 * pi34};
+  // f: 2 sqrt(2) pi^-3/4 (the xyz component); the per-component ratios are applied by the
+  // generic kernel (pcg_norm_ratio)
+  const double lnorm[4] = {pi34, std::sqrt(2.0) * pi34, 2.0 * pi34, 2.0 * std::sqrt(2.0) * pi34};
   const double pf_half = std::pow(2.0 / M_PI, 0.25) * std::pow(2.0, 0.25);   // ... and the sqrt(2) of sqrt(2 theta^2)
   for (int i = 0; i < n; ++i) {
     const HostPair& p = h->pairs[k->pairs[i]];
@@ -583,15 +604,95 @@ void fill_item(PcItem& I, const Kind* kb, const Kind* kk) {
   I.ket = kk->view();
 }
 
-cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, cudaStream_t st) {
-  pc_launch_fn fn = pc_launch_table[h->cart_d ? 1 : 0][pcb][pck];
-  if (!fn) return cudaErrorInvalidValue;
-  static const int pair_l[6] = {0, 1, 2, 2, 3, 4};      // ss ps pp ds dp dd
-  A.boys = h->boys_l[pair_l[pcb] + pair_l[pck]].p;
+// flop model per primitive / per contracted quartet: the generator's tables for the
+// s, p, d classes, the same counting on the loop form for classes with an f shell
+double flop_prim(int pcb, int pck) {
+  if (pcb < PC_NPC_GEN && pck < PC_NPC_GEN) return pc_flop_prim_table[pcb][pck];
+  const int La = pair_L(pcb), Lc = pair_L(pck), L = La + Lc;
+  double elems = 0;
+  for (int la = 0; la <= La; ++la)
+    for (int lc = 0; lc <= Lc; ++lc) elems += (double)ncart(la) * ncart(lc) * (L + 1 - la - lc);
+  return 9.0 * (L + 1) + 12.0 + 2.0 * 3.5 * elems;       // ~3.5 base references per VRR element
+}
+double flop_cont(int pcb, int pck) {
+  if (pcb < PC_NPC_GEN && pck < PC_NPC_GEN) return pc_flop_cont_table[pcb][pck];
+  int l[4];
+  class_l(pcb, l[0], l[1]);
+  class_l(pck, l[2], l[3]);
+  const double nbc = (double)ncart(l[0]) * ncart(l[1]), nkc = (double)ncart(l[2]) * ncart(l[3]);
+  const double ne = pcg_ncum(l[0] + l[1]) - pcg_ncum(l[0] - 1), nf = pcg_ncum(l[2] + l[3]) - pcg_ncum(l[2] - 1);
+  // HRR levels (2 flop per element, ~ly levels of ~block size) + the two transforms
+  return 2.0 * (ne * nkc * std::max(1, l[3]) + nkc * nbc * std::max(1, l[1])) + 4.0 * nbc * nkc;
+}
+
+// scratch layout of the generic kernel for one class (see pcg_quartet); returns words per thread
+size_t gen_class_layout(const pc_basis* h, int pcb, int pck, PcGenClass& C) {
+  memset(&C, 0, sizeof(C));
+  class_l(pcb, C.lx1, C.ly1);
+  class_l(pck, C.lx2, C.ly2);
+  C.nx1 = h->nfun(C.lx1); C.ny1 = h->nfun(C.ly1); C.nx2 = h->nfun(C.lx2); C.ny2 = h->nfun(C.ly2);
+  C.cart_d = h->cart_d ? 1 : 0;
+  C.scat = h->ints_type == 1 ? 1 : 0;
+  const int La = C.lx1 + C.ly1, Lc = C.lx2 + C.ly2;
+  C.L = La + Lc;
+  int off = 0;
+  for (int la = 0; la <= La; ++la)
+    for (int lc = 0; lc <= Lc; ++lc) {
+      C.offV[la][lc] = off;
+      off += ncart(la) * ncart(lc) * (C.L + 1 - la - lc);
+    }
+  const int ne = pcg_ncum(La) - pcg_ncum(C.lx1 - 1), nf = pcg_ncum(Lc) - pcg_ncum(C.lx2 - 1);
+  const int nbc = ncart(C.lx1) * ncart(C.ly1), nkc = ncart(C.lx2) * ncart(C.ly2);
+  const int nsb = C.nx1 * C.ny1, nsk = C.nx2 * C.ny2;
+  C.offT1 = 0;
+  C.offG = ne * nkc;
+  C.sizeA = std::max(off, std::max(ne * nkc + nbc * nkc, nsb * nsk));
+  C.sizeB = std::max(ne * nf, nbc * nsk);
+  return (size_t)C.sizeA + C.sizeB;
+}
+
+// threads of a generic launch: whole 64-thread blocks, enough for the tasks, bounded by the
+// scratch budget (PYCHEM_B200_GENERIC_SCRATCH_MB per launch, default 512)
+int gen_thread_count(long long nwarps, size_t words) {
+  size_t mb = 512;
+  if (const char* e = getenv("PYCHEM_B200_GENERIC_SCRATCH_MB"))
+    if (atoll(e) > 0) mb = (size_t)atoll(e);
+  long long cap = (long long)((mb << 20) / (words * sizeof(double)));
+  cap = std::max<long long>(64, cap / 64 * 64);
+  cap = std::min<long long>(cap, 148LL * 16 * 64);            // 16 blocks of 64 per SM
+  const long long want = (nwarps * 32 + 63) / 64 * 64;
+  return (int)std::max<long long>(64, std::min(cap, want));
+}
+
+// `scratch`/`gen_threads`: the generic kernel's scratch (classes with an f shell); null = the
+// handle's own buffer, grown on demand (explicit task lists, all on h->stream)
+cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, cudaStream_t st,
+                        DevBuf<double>* scratch = nullptr, int gen_threads = 0) {
+  A.boys = h->boys_l[pair_L(pcb) + pair_L(pck)].p;
   A.nbf = h->nbf;
   A.scat_S = h->grid;
   A.thresh = h->thresh;
-  cudaError_t e = fn(mode, A, st ? st : h->stream);
+  cudaError_t e;
+  if (h->generic(pcb, pck)) {
+    PcGenClass C;
+    const size_t words = gen_class_layout(h, pcb, pck, C);
+    if (!scratch) {
+      scratch = &h->gen_scratch;
+      gen_threads = gen_thread_count(A.nwarps, words);
+      if (scratch->n < words * (size_t)gen_threads) {
+        e = cudaStreamSynchronize(h->stream);                  // an earlier launch may still use it
+        if (e == cudaSuccess) e = scratch->alloc(words * (size_t)gen_threads);
+        if (e != cudaSuccess) return e;
+      }
+    }
+    C.scratch = scratch->p;
+    C.nthreads = gen_threads;
+    e = pc_launch_generic(mode, A, C, st ? st : h->stream);
+  } else {
+    pc_launch_fn fn = pc_launch_table[h->cart_d ? 1 : 0][pcb][pck];
+    if (!fn) return cudaErrorInvalidValue;
+    e = fn(mode, A, st ? st : h->stream);
+  }
   if (e == cudaSuccess) h->launches += 1;
   return e;
 }
@@ -630,7 +731,7 @@ int launch_group(pc_basis* h, int mode, const LaunchGroup& g, PcEriArgs& A, cuda
   A.nwarps = warp;
   A.ex_bra = nullptr;
   A.ex_ket = nullptr;
-  cudaError_t e = launch_args(h, mode, g.pcb, g.pck, A, st);
+  cudaError_t e = launch_args(h, mode, g.pcb, g.pck, A, st, g.scratch, g.gen_threads);
   if (e != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(e));
   return 0;
 }
@@ -710,6 +811,7 @@ void build_segments_host(const std::vector<double>& pmB, const std::vector<int>&
 // PYCHEM_B200_RUN="4" (all of them) or "psss=4,ssss=8,..." (per class; classes not named keep
 // their default).
 int run_length(const pc_basis* h, int pcb, int pck) {
+  if (h->generic(pcb, pck)) return 1;            // the generic kernel takes one quartet per thread
   int r = pc_run_table[h->cart_d ? 1 : 0][pcb][pck];
   if (r <= 1) return 1;                          // not a run kernel
   const char* e = getenv("PYCHEM_B200_RUN");
@@ -770,9 +872,12 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; return fail(cudaGetErrorString(e)); }
   h->nshell = nshell;
+  if (const char* fg = getenv("PYCHEM_B200_FORCE_GENERIC")) h->force_generic = atoi(fg) != 0;
   int poff = 0, n_d = 0;
   for (int s = 0; s < nshell; ++s) {
-    if (l[s] < 0 || l[s] > 2) { delete h; return fail("pc_basis_create: only s, p, d shells are supported by this build"); }
+    if (l[s] < 0 || l[s] > PCG_LMAX) { delete h; return fail("pc_basis_create: only s, p, d, f shells are supported by this build"); }
+    if (l[s] == 3 && is_cart[s]) { delete h; return fail("pc_basis_create: Cartesian f shells are not supported (Cartesian_L = [2] only)"); }
+    h->max_l = std::max(h->max_l, l[s]);
     if (l[s] == 2) {
       // Cartesian_L = [2] (Util/structures.py:844-849) applies to every d shell of the molecule
       if (n_d == 0) h->cart_d = is_cart[s] != 0;
@@ -841,7 +946,7 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
   // The ERI kernels of one class read the orders m = 0..L of ONE interval: per-L copies with the
   // orders of an interval adjacent ((L+1) x 32 bytes contiguous) cost one cache line per lookup
   // instead of L+1 lines 248 KB apart.
-  for (int L = 0; L <= PC_BOYS_LMAX && e == cudaSuccess; ++L) {
+  for (int L = 0; L <= 4 * h->max_l && e == cudaSuccess; ++L) {
     std::vector<double> t((size_t)PC_BOYS_NPOINTS * (L + 1) * 4);
     for (int j = 0; j < PC_BOYS_NPOINTS; ++j)
       for (int m = 0; m <= L; ++m)
@@ -987,6 +1092,8 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     h->plan_bufs.clear();
     for (auto* b : h->plan_ibufs) delete b;
     h->plan_ibufs.clear();
+    for (auto* b : h->gen_bufs) delete b;
+    h->gen_bufs.clear();
     h->plan.clear();
     h->my_quartets = h->my_eris = h->all_quartets = h->all_eris = 0;
     // ---- phase A (host threads): the segments of every (bra bucket, ket bucket) ------------
@@ -1046,10 +1153,10 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
       const double nsph = (double)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);
-      return pc_flop_cont_table[B->pc][Kt->pc] + 40.0 * nsph + 60.0;
+      return flop_cont(B->pc, Kt->pc) + 40.0 * nsph + 60.0;
     };
     auto cost_total = [&](const PlanItem& it) {
-      return it.prim_exec * pc_flop_prim_table[h->kinds[it.kb]->pc][h->kinds[it.kk]->pc] +
+      return it.prim_exec * flop_prim(h->kinds[it.kb]->pc, h->kinds[it.kk]->pc) +
              (double)it.total_q * quartet_cost(it);
     };
     // every bucket pair is cut into nranks contiguous slices of equal modelled cost, at segment
@@ -1059,7 +1166,7 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
     for (size_t k = 0; k < h->plan.size(); ++k) {
       PlanItem& it = h->plan[k];
       const Work& w = work[widx[k]];
-      const double fp = pc_flop_prim_table[h->kinds[it.kb]->pc][h->kinds[it.kk]->pc], fq = quartet_cost(it);
+      const double fp = flop_prim(h->kinds[it.kb]->pc, h->kinds[it.kk]->pc), fq = quartet_cost(it);
       auto seg_cost = [&](int sg) { return w.seg_prim[sg] * fp + (double)w.seg_q[sg] * fq; };
       auto cut = [&](int r) {           // first segment of rank r's slice
         if (r <= 0) return 0;
@@ -1133,6 +1240,19 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       }
       std::stable_sort(h->groups.begin(), h->groups.end(),
                        [](const LaunchGroup& a, const LaunchGroup& b) { return a.cost > b.cost; });
+      // classes with an f shell: every launch group owns the scratch of its generic kernel
+      for (LaunchGroup& g : h->groups) {
+        if (!h->generic(g.pcb, g.pck)) continue;
+        long long nwarps = 0;
+        for (int idx : g.items) nwarps += (h->plan[idx].count + 31) / 32;
+        if (nwarps == 0) continue;
+        PcGenClass C;
+        const size_t words = gen_class_layout(h, g.pcb, g.pck, C);
+        g.gen_threads = gen_thread_count(nwarps, words);
+        g.scratch = new DevBuf<double>();
+        h->gen_bufs.push_back(g.scratch);
+        PC_CUDA(g.scratch->alloc(words * (size_t)g.gen_threads));
+      }
     }
     h->planned = true;
     h->plan_id += 1;
@@ -1617,7 +1737,8 @@ int pc_one_electron(pc_basis* h, int natom, const double* Z, const double* R, do
   double* o = h->ostage.p;
   double* dcore = is_device_ptr(core) ? core : o;
   double* dov = is_device_ptr(overlap) ? overlap : o + nn;
-  one_electron_kernel<<<(S.npair + 63) / 64, 64, 0, h->stream>>>(S, natom, dzr.p, dzr.p + natom, h->boys.p, dcore, dov);
+  if (h->max_l <= 2) one_electron_kernel<2><<<(S.npair + 63) / 64, 64, 0, h->stream>>>(S, natom, dzr.p, dzr.p + natom, h->boys.p, dcore, dov);
+  else one_electron_kernel<3><<<(S.npair + 63) / 64, 64, 0, h->stream>>>(S, natom, dzr.p, dzr.p + natom, h->boys.p, dcore, dov);
   PC_CUDA(cudaGetLastError());
   h->launches += 1;
   if (dcore != core) { if (copy_out(h, dcore, core)) return 1; }

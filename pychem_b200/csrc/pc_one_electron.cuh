@@ -39,9 +39,16 @@ __device__ __forceinline__ void pc1_comp(int l, int k, int& lx, int& ly, int& lz
   lx = ly = lz = 0;
 }
 
-// (Gamma(n + 1/2))^-1/2 for n = 0, 1, 2   (Util/structures.py:850-856)
+// packed index of the Hermite triple (t, u, v): triples ordered by their total, then like the
+// Cartesian components of a shell
+__device__ __forceinline__ int pc1_tuv(int t, int u, int v) {
+  const int tot = t + u + v, s = u + v;
+  return tot * (tot + 1) * (tot + 2) / 6 + s * (s + 1) / 2 + v;
+}
+
+// (Gamma(n + 1/2))^-1/2 for n = 0..3   (Util/structures.py:850-856)
 __device__ __forceinline__ double pc1_gnorm(int n) {
-  return n == 0 ? 0.75112554446494248 : (n == 1 ? 1.0622519320271969 : 0.86732507058407751);
+  return n == 0 ? 0.75112554446494248 : (n == 1 ? 1.0622519320271969 : (n == 2 ? 0.86732507058407751 : 0.5485445389623983));
 }
 
 // unscaled Boys function F_m(T), m = 0..L, with the reference's three branches
@@ -68,11 +75,13 @@ __device__ __forceinline__ void pc1_boys(int L, double T, double R2, const doubl
 }
 
 // Hermite expansion coefficients of one dimension: E[i][j][t], i <= la, j <= lbmax
+// (LM = highest shell angular momentum the instantiation serves: 2 for s, p, d; 3 with f shells)
+template <int LM>
 __device__ __forceinline__ void pc1_hermite(int la, int lbmax, double PA, double PB, double inv2p,
-                                            double (&E)[3][5][8]) {
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 5; ++j)
-      for (int t = 0; t < 8; ++t) E[i][j][t] = 0.0;
+                                            double (&E)[LM + 1][LM + 3][2 * LM + 4]) {
+  for (int i = 0; i < LM + 1; ++i)
+    for (int j = 0; j < LM + 3; ++j)
+      for (int t = 0; t < 2 * LM + 4; ++t) E[i][j][t] = 0.0;
   E[0][0][0] = 1.0;
   for (int i = 0; i < la; ++i)
     for (int t = 0; t <= i + 1; ++t) {
@@ -89,6 +98,7 @@ __device__ __forceinline__ void pc1_hermite(int la, int lbmax, double PA, double
       }
 }
 
+template <int LM>
 __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int natom, const double* __restrict__ Z,
                                                          const double* __restrict__ Rc,
                                                          const double* __restrict__ boys,
@@ -105,10 +115,13 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
   const double Bx = S.A[3 * b], By = S.A[3 * b + 1], Bz = S.A[3 * b + 2];
   const double r2 = (Ax - Bx) * (Ax - Bx) + (Ay - By) * (Ay - By) + (Az - Bz) * (Az - Bz);
   const int L = la + lb;
-  double Sc[36], Tc[36], Vc[36];
-  for (int k = 0; k < 36; ++k) Sc[k] = Tc[k] = Vc[k] = 0.0;
-  double Ex[3][5][8], Ey[3][5][8], Ez[3][5][8];
-  double Rt[5][5][5][5];     // R^n_{tuv}, n + t + u + v <= L
+  constexpr int NC2 = ((LM + 1) * (LM + 2) / 2) * ((LM + 1) * (LM + 2) / 2);     // Cartesian block
+  constexpr int NR = 2 * LM + 1;
+  double Sc[NC2], Tc[NC2], Vc[NC2];
+  for (int k = 0; k < NC2; ++k) Sc[k] = Tc[k] = Vc[k] = 0.0;
+  double Ex[LM + 1][LM + 3][2 * LM + 4], Ey[LM + 1][LM + 3][2 * LM + 4], Ez[LM + 1][LM + 3][2 * LM + 4];
+  constexpr int NTUV = NR * (NR + 1) * (NR + 2) / 6;       // (t, u, v) with t + u + v <= 2 LM
+  double Rt[NR][NTUV];           // R^n_{tuv}, n + t + u + v <= L, (t, u, v) packed by pc1_tuv
   for (int ia = 0; ia < S.K[a]; ++ia)
     for (int ib = 0; ib < S.K[b]; ++ib) {
       const double al = S.exps[S.poff[a] + ia], be = S.exps[S.poff[b] + ib];
@@ -118,9 +131,9 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
       const double U = pow(M_PI * sigma, 1.5) * exp(-al * be * sigma * r2);     // incl. (pi/p)^1.5
       const double Px = (al * Ax + be * Bx) * sigma, Py = (al * Ay + be * By) * sigma, Pz = (al * Az + be * Bz) * sigma;
       const double inv2p = 0.5 * sigma;
-      pc1_hermite(la, lb + 2, Px - Ax, Px - Bx, inv2p, Ex);
-      pc1_hermite(la, lb + 2, Py - Ay, Py - By, inv2p, Ey);
-      pc1_hermite(la, lb + 2, Pz - Az, Pz - Bz, inv2p, Ez);
+      pc1_hermite<LM>(la, lb + 2, Px - Ax, Px - Bx, inv2p, Ex);
+      pc1_hermite<LM>(la, lb + 2, Py - Ay, Py - By, inv2p, Ey);
+      pc1_hermite<LM>(la, lb + 2, Pz - Az, Pz - Bz, inv2p, Ez);
       // ---- overlap and kinetic energy (one_electron_kinetic.c:62-66) ----
       for (int ka = 0; ka < na; ++ka) {
         int ax, ay, az;
@@ -144,11 +157,11 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
       for (int c = 0; c < natom; ++c) {
         const double X = Px - Rc[3 * c], Y = Py - Rc[3 * c + 1], Zc = Pz - Rc[3 * c + 2];
         const double R2 = X * X + Y * Y + Zc * Zc;
-        double F[5];
+        double F[NR];
         pc1_boys(L, zeta * R2, R2, boys, F);
         double m2p = 1.0;
         for (int n = 0; n <= L; ++n) {
-          Rt[n][0][0][0] = m2p * F[n];
+          Rt[n][0] = m2p * F[n];
           m2p *= -2.0 * zeta;
         }
         for (int tot = 1; tot <= L; ++tot)
@@ -157,10 +170,10 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
               const int v = tot - t - u;
               for (int n = 0; n <= L - tot; ++n) {
                 double val;
-                if (t > 0) val = (t > 1 ? (t - 1) * Rt[n + 1][t - 2][u][v] : 0.0) + X * Rt[n + 1][t - 1][u][v];
-                else if (u > 0) val = (u > 1 ? (u - 1) * Rt[n + 1][t][u - 2][v] : 0.0) + Y * Rt[n + 1][t][u - 1][v];
-                else val = (v > 1 ? (v - 1) * Rt[n + 1][t][u][v - 2] : 0.0) + Zc * Rt[n + 1][t][u][v - 1];
-                Rt[n][t][u][v] = val;
+                if (t > 0) val = (t > 1 ? (t - 1) * Rt[n + 1][pc1_tuv(t - 2, u, v)] : 0.0) + X * Rt[n + 1][pc1_tuv(t - 1, u, v)];
+                else if (u > 0) val = (u > 1 ? (u - 1) * Rt[n + 1][pc1_tuv(t, u - 2, v)] : 0.0) + Y * Rt[n + 1][pc1_tuv(t, u - 1, v)];
+                else val = (v > 1 ? (v - 1) * Rt[n + 1][pc1_tuv(t, u, v - 2)] : 0.0) + Zc * Rt[n + 1][pc1_tuv(t, u, v - 1)];
+                Rt[n][pc1_tuv(t, u, v)] = val;
               }
             }
         const double pf = -Z[c] * spf * w;
@@ -174,7 +187,7 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
             for (int t = 0; t <= ax + bx; ++t)
               for (int u = 0; u <= ay + by; ++u)
                 for (int v = 0; v <= az + bz; ++v)
-                  sum += Ex[ax][bx][t] * Ey[ay][by][u] * Ez[az][bz][v] * Rt[0][t][u][v];
+                  sum += Ex[ax][bx][t] * Ey[ay][by][u] * Ez[az][bz][v] * Rt[0][pc1_tuv(t, u, v)];
             Vc[ka * nb + kb] += pf * sum;
           }
         }
@@ -183,7 +196,7 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
   // ---- angular normalisation, cart -> spherical, scatter (integrals.py:345-357) ----
   // nuclear fundamentals of the reference carry (pi sigma)^1.5 inside U and the Hermite sum gives
   // (2 pi / zeta) K_ab ... : -Z sqrt(2/pi) (pi sigma)^1.5 sqrt(2 zeta) = -Z 2 pi / zeta, as it must
-  double core_c[36], ov_c[36];
+  double core_c[NC2], ov_c[NC2];
   for (int ka = 0; ka < na; ++ka) {
     int ax, ay, az;
     pc1_comp(la, ka, ax, ay, az);
@@ -200,17 +213,26 @@ __global__ void __launch_bounds__(64) one_electron_kernel(PcShellTable S, int na
   const double C2S[5][6] = {{0.86602540378443865, 0, 0, -0.86602540378443865, 0, 0},
                             {0, 1, 0, 0, 0, 0}, {0, 0, 1, 0, 0, 0}, {0, 0, 0, 0, 1, 0},
                             {-0.5, 0, 0, -0.5, 0, 1}};
-  const bool sa = (la == 2 && !S.cart_d), sb = (lb == 2 && !S.cart_d);
-  const int nfa = sa ? 5 : na, nfb = sb ? 5 : nb;
+  // spherical f (Data/transform_basis.py:13-19), rows over cart xxx xxy xxz xyy xyz xzz yyy yyz yzz zzz
+  const double C2SF[7][10] = {
+      {0.7905694150420949, 0, 0, -1.0606601717798212, 0, 0, 0, 0, 0, 0},
+      {0, 1.0606601717798212, 0, 0, 0, 0, -0.7905694150420949, 0, 0, 0},
+      {0, 0, 0.8660254037844386, 0, 0, 0, 0, -0.8660254037844386, 0, 0},
+      {0, 0, 0, 0, 1, 0, 0, 0, 0, 0},
+      {-0.6123724356957945, 0, 0, -0.27386127875258304, 0, 1.0954451150103321, 0, 0, 0, 0},
+      {0, -0.27386127875258304, 0, 0, 0, 0, -0.6123724356957945, 0, 1.0954451150103321, 0},
+      {0, 0, -0.6708203932499369, 0, 0, 0, 0, -0.6708203932499369, 0, 1}};
+  const bool sa = (la == 2 && !S.cart_d) || (LM >= 3 && la == 3), sb = (lb == 2 && !S.cart_d) || (LM >= 3 && lb == 3);
+  const int nfa = sa ? 2 * la + 1 : na, nfb = sb ? 2 * lb + 1 : nb;
   const int fa = S.first_fn[a], fb = S.first_fn[b];
   for (int ma = 0; ma < nfa; ++ma)
     for (int mb = 0; mb < nfb; ++mb) {
       double cv = 0.0, sv = 0.0;
       for (int ka = 0; ka < na; ++ka) {
-        const double ca = sa ? C2S[ma][ka] : (ka == ma ? 1.0 : 0.0);
+        const double ca = sa ? ((LM >= 3 && la == 3) ? C2SF[ma][ka] : C2S[ma][ka]) : (ka == ma ? 1.0 : 0.0);
         if (ca == 0.0) continue;
         for (int kb = 0; kb < nb; ++kb) {
-          const double cb = sb ? C2S[mb][kb] : (kb == mb ? 1.0 : 0.0);
+          const double cb = sb ? ((LM >= 3 && lb == 3) ? C2SF[mb][kb] : C2S[mb][kb]) : (kb == mb ? 1.0 : 0.0);
           if (cb == 0.0) continue;
           cv += ca * cb * core_c[ka * nb + kb];
           sv += ca * cb * ov_c[ka * nb + kb];

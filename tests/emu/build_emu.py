@@ -112,7 +112,7 @@ def build(jobs=None, regenerate=True):
         with contextlib.redirect_stdout(io.StringIO()):
             gen_eri.main(GEN)
     csrc_out = os.path.join(SRC, "pychem_b200", "csrc")
-    headers = ["pc_common.cuh", "pc_one_electron.cuh"]
+    headers = ["pc_common.cuh", "pc_one_electron.cuh", "pc_generic.cuh", "pc_generic_class.h"]
     dep = hashlib.sha1()
     for hname in headers:
         t = transform(open(os.path.join(CSRC, hname)).read(), hname)
@@ -125,6 +125,10 @@ def build(jobs=None, regenerate=True):
     units = []
     t = transform(open(os.path.join(CSRC, "pc_api.cu")).read(), "pc_api.cu")
     p = os.path.join(csrc_out, "pc_api.cpp")
+    _write_if_changed(p, t)
+    units.append(p)
+    t = transform(open(os.path.join(CSRC, "pc_generic.cu")).read(), "pc_generic.cu")
+    p = os.path.join(csrc_out, "pc_generic.cpp")
     _write_if_changed(p, t)
     units.append(p)
     p = os.path.join(csrc_out, "pc_mp2_stub.cpp")

@@ -8,6 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 H2 = [["H", 1.0, 0.0, 0.0, 0.0], ["H", 1.0, 0.0, 0.0, 1.0]]              # Tests/H2_HF.test.inp
 LIH = [["Li", 3.0, 0.0, 0.0, 0.0], ["H", 1.0, 2.2, 0.0, 0.0]]            # Tests/LiH_SFS_NOCI.test.inp
 H3 = [["H", 1.0, 0.0, 0.0, 0.0], ["H", 1.0, 1.0, 0.0, 0.0], ["H", 1.0, 0.4, 1.0, 0.0]]  # Tests/example1.inp
+# f-shell cases (oracle/make_golden_f.py): four heavy atoms at general positions; hydrogen fluoride
+CNON = [["C", 6.0, 0.00, 0.00, 0.00], ["N", 7.0, 1.05, 0.35, -0.20], ["O", 8.0, -0.40, 1.15, 0.55],
+        ["N", 7.0, 0.60, -0.85, 1.10]]
+HYDROGEN_FLUORIDE = [["F", 9.0, 0.0, 0.0, 0.0], ["H", 1.0, 0.31, 0.42, 0.74]]
 
 
 def molecule(name):
@@ -23,7 +27,24 @@ def molecule(name):
         return S.Molecule(S.water_cluster(2), "6-31G**")
     if name == "benzene":
         return S.Molecule(S.benzene(), "6-31G*")
+    if name == "cnon_tz":
+        return S.Molecule(CNON, "cc-pVTZ")
+    if name == "hf_tz":
+        return S.Molecule(HYDROGEN_FLUORIDE, "cc-pVTZ")
     raise KeyError(name)
+
+
+def f_shell_targets(g):
+    """(quartet, target block, source) for every sampled quartet of tests/golden/f_shell_ccpvtz.npz:
+    the reference's own block where the reference is right; for (d f) pairs in goofy order, where its
+    HRR stride is off by one (Methods/c_ints/two_electron_hrr.c:18), the block of the reference
+    with that one expression corrected -- which agrees with independent McMurchie-Davidson values
+    to 5e-15 (oracle/make_golden_f.py; tests/test_oracle.py checks the stored evidence)."""
+    out = []
+    for q, lo, hi, bad in zip(g["quartets"], g["offsets"][:-1], g["offsets"][1:], g["affected"]):
+        src = g["fixed_blocks"] if bad else g["blocks"]
+        out.append((tuple(int(x) for x in q), src[lo:hi], "reference, HRR stride corrected" if bad else "reference"))
+    return out
 
 
 def bounds_from_flat(table, flat):

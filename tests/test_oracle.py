@@ -122,3 +122,54 @@ def test_scattering_integrals_match_reference(gold):
         assert abs(g["intensity"][0] - 100.0) < 1e-9      # S = 0: N_el^2
     finally:
         oracle.set_ints_type(0, -1.0)
+
+
+def test_f_shell_quartets_reference_and_independent_values(gold):
+    """l = 3: the restatement against the reference (every class with an f shell, four centres).
+    For (d f) pairs in goofy order the reference's HRR stride is off by one (two_electron_hrr.c:18);
+    there the target is the reference with that expression corrected, and the fixture carries the
+    evidence for the diagnosis: independent McMurchie-Davidson values (oracle/md_eri.py) agree with
+    the corrected reference everywhere and with the stock reference on all unaffected quartets."""
+    g = gold("f_shell_ccpvtz.npz")
+    assert float(g["md_vs_reference_unaffected"]) < ERI_TOL     # the yardstick agrees with the stock reference elsewhere
+    assert float(g["fixed_vs_md"]) < ERI_TOL                    # ... and with the corrected one on the affected quartets
+    assert float(g["fixed_vs_reference_unaffected"]) == 0.0     # the correction changes nothing else
+    tb = BasisTable(helpers.molecule("cnon_tz"))
+    ob = oracle.OracleBasis(tb)
+    classes, n_fixed = set(), 0
+    for (a, b, c, d), target, source in helpers.f_shell_targets(g):
+        blk = ob.quartet(a, b, c, d).ravel()
+        assert blk.size == target.size
+        assert np.abs(blk - target).max() < ERI_TOL, ((a, b, c, d), source)
+        n_fixed += source != "reference"
+        if max(tb.l[a], tb.l[b], tb.l[c], tb.l[d]) == 3:
+            classes.add(tuple(sorted([tuple(sorted((tb.l[a], tb.l[b]))), tuple(sorted((tb.l[c], tb.l[d])))])))
+    assert len(classes) == 34 and n_fixed >= 10       # every class with an f shell; the affected pairs are covered
+    # independent values, directly
+    pos = {tuple(int(x) for x in q): k for k, q in enumerate(g["quartets"])}
+    for q, lo, hi in zip(g["md_quartets"], g["md_offsets"][:-1], g["md_offsets"][1:]):
+        a, b, c, d = (int(x) for x in q)
+        assert np.abs(ob.quartet(a, b, c, d).ravel() - g["md_blocks"][lo:hi]).max() < ERI_TOL
+        assert (a, b, c, d) in pos
+    # the stock reference's (d f) blocks are off by the size of the integrals themselves
+    bad = [k for k, f in enumerate(g["affected"]) if f]
+    a, b, c, d = (int(x) for x in g["quartets"][bad[0]])
+    lo, hi = g["offsets"][bad[0]], g["offsets"][bad[0] + 1]
+    assert np.abs(ob.quartet(a, b, c, d).ravel() - g["blocks"][lo:hi]).max() > 1e-6
+
+
+def test_f_shell_md_yardstick_matches_reference_live():
+    """oracle/md_eri.py against the live reference on an unaffected f quartet (needs oracle/_ref)."""
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not built")
+    from oracle import md_eri
+    ns = ref_driver.modules()
+    from Data import transform_basis
+    mol, _ = ref_driver.build_molecule(helpers.CNON, "cc-pVTZ")
+    shells = [(np.array(at.Coordinates, dtype=float), int(cg.AngularMomentum), list(cg.Exponents), list(cg.ScaledCCs),
+               list(cg.ContractionScaling)) for at in mol.Atoms for cg in at.Basis]
+    q = (9, 19, 3, 13)                # (f f | s s) on two centres, single primitives
+    ref = np.asarray(ns.integrals.two_electron(mol.ShellPairs[q[:2]], mol.ShellPairs[q[2:]], 0, -1.0))
+    with np.errstate(all="ignore"):
+        md = md_eri.shell_quartet([shells[s] for s in q], transform_basis.cart_to_spher)
+    assert np.abs(md - ref).max() < ERI_TOL

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref", "pychem_py3"))
 from Data import basis  # noqa: E402
 
-SETS = ["STO3G", "321G", "631G", "631GS", "631GSS", "6311G", "6311GSS", "CCPVDZ"]
+SETS = ["STO3G", "321G", "631G", "631GS", "631GSS", "6311G", "6311GSS", "CCPVDZ", "CCPVTZ"]
 ELEMENTS = ["H", "HE", "LI", "BE", "B", "C", "N", "O", "F", "NE"]
 
 out = {}
