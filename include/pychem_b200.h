@@ -37,7 +37,9 @@ int pc_device_count(int* count);
  *   Replaces: ContractedGaussian constants (Util/structures.py:834-856), the eager ShellPair
  *   construction (Util/structures.py:510-523, 918-956) and _c_ints.shellpair_quantities
  *   (Methods/_c_ints.c:120-155, Methods/c_ints/shellpair_quantities.c:5-38).
- *   l[s] <= 2 (s, p, d); d shells either all spherical or all Cartesian (is_cart, Cartesian_L).
+ *   l[s] <= 3 (s, p, d, f); d shells either all spherical or all Cartesian (is_cart, Cartesian_L);
+ *   f shells spherical.  Quartets of s/p/d shells run the generated class kernels, quartets with
+ *   an f shell the generic kernel (csrc/pc_generic.cuh); g and higher are refused.
  *   scc = cc*(2a)^((l+1.5)/2) (Util/structures.py:843); first_fn = index of the shell's first
  *   basis function (atoms -> shells -> functions, Util/structures.py:511-520).
  */
