@@ -87,6 +87,8 @@ struct HostPair {
   int swapped;    // x == b
   int kind, pos;  // bucket and position inside it
   double pmax;
+  size_t prim_off;  // first record of this pair in pc_basis::prim_host (6 doubles per primitive pair)
+  int keff;         // significant primitive pairs
 };
 
 struct Kind {
@@ -451,6 +453,7 @@ struct pc_basis {
   std::vector<Shell> shells;
   std::vector<double> exps, scc;
   std::vector<HostPair> pairs;  // upper-triangular order
+  std::vector<double> prim_host; // per pair, most significant primitive first: {sigma, Ucc, Px, Py, Pz, kz}
   std::vector<Kind*> kinds;
   DevBuf<double> boys;                  // [m][j][4]  (one-electron kernel)
   DevBuf<double> boys_l[4 * PCG_LMAX + 1];   // per total angular momentum L: [j][m = 0..L][4] (ERI kernels)
@@ -523,13 +526,31 @@ struct pc_basis {
 
 namespace {
 
-// (re)build and upload the SoA tables of one bucket in its current pair order
-// primitive-pair quantities: Methods/c_ints/shellpair_quantities.c:23-36
-int upload_kind(pc_basis* h, Kind* k) {
-  const int n = (int)k->pairs.size();
-  const int K = k->K;
-  std::vector<int> fx(n), fy(n), pid(n), keff(n);
-  std::vector<double> xy((size_t)3 * n), prim((size_t)6 * K * n);
+// run fn(0..n-1) on up to 16 host threads
+void parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+  const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < 2 || hw == 1) {
+    for (size_t k = 0; k < n; ++k) fn(k);
+    return;
+  }
+  std::atomic<size_t> next(0);
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < hw; ++t)
+    pool.emplace_back([&]() {
+      for (size_t k = next.fetch_add(1); k < n; k = next.fetch_add(1)) fn(k);
+    });
+  for (auto& th : pool) th.join();
+}
+
+// primitive-pair quantities of every shell pair (Methods/c_ints/shellpair_quantities.c:23-36),
+// computed once per geometry on the host threads; upload_kind only gathers them in bucket order
+void compute_pair_prims(pc_basis* h) {
+  size_t off = 0;
+  for (HostPair& p : h->pairs) {
+    p.prim_off = off;
+    off += (size_t)h->shells[p.a].K * h->shells[p.b].K;
+  }
+  h->prim_host.assign(off * 6, 0.0);
   // uniform normalisation constants folded into the pair prefactor (structures.py:850-856):
   // s: pi^-3/4, p: sqrt(2) pi^-3/4, d: 2 pi^-3/4 (the xy-type d component; xx-type ratio 1/sqrt3
   // lives in the generated cart->spherical code); sqrt(sqrt(2/pi)) per pair gives the
@@ -539,6 +560,57 @@ int upload_kind(pc_basis* h, Kind* k) {
   // generic kernel (pcg_norm_ratio)
   const double lnorm[4] = {pi34, std::sqrt(2.0) * pi34, 2.0 * pi34, 2.0 * std::sqrt(2.0) * pi34};
   const double pf_half = std::pow(2.0 / M_PI, 0.25) * std::pow(2.0, 0.25);   // ... and the sqrt(2) of sqrt(2 theta^2)
+  const size_t chunk = 256;
+  parallel_for((h->pairs.size() + chunk - 1) / chunk, [&](size_t c) {
+    struct PP { double sigma, ucc, P[3], kz; };
+    std::vector<PP> pp;
+    for (size_t ip = c * chunk; ip < std::min(h->pairs.size(), (c + 1) * chunk); ++ip) {
+      HostPair& p = h->pairs[ip];
+      const Shell& X = h->shells[p.x];
+      const Shell& Y = h->shells[p.y];
+      double r2 = 0;
+      for (int c3 = 0; c3 < 3; ++c3) {
+        const double d = X.A[c3] - Y.A[c3];
+        r2 += d * d;
+      }
+      const double cn = lnorm[X.l] * lnorm[Y.l] * pf_half;
+      // primitive pairs of this shell pair, most significant first.  Pairs whose prefactor
+      // U*cc is below PC_PRIM_EPS contribute < 1e-20 to any integral (two-centre pairs of tight
+      // primitives: U = exp(-ab/(a+b) r^2) underflows) and are cut off by keff.  The reference
+      // visits them all (no primitive screening); the results differ by < 1e-16.
+      pp.clear();
+      for (int ia = 0; ia < X.K; ++ia)
+        for (int ib = 0; ib < Y.K; ++ib) {
+          const double a = h->exps[X.poff + ia], b = h->exps[Y.poff + ib];
+          PP e;
+          e.sigma = 1.0 / (a + b);
+          const double U = std::pow(M_PI * e.sigma, 1.5) * std::exp(-a * b * e.sigma * r2);
+          e.ucc = U * h->scc[X.poff + ia] * h->scc[Y.poff + ib] * cn;
+          for (int c3 = 0; c3 < 3; ++c3) e.P[c3] = (a * X.A[c3] + b * Y.A[c3]) * e.sigma;
+          e.kz = b * e.sigma;  // kappa*zeta = (2b)(sigma/2)
+          pp.push_back(e);
+        }
+      std::stable_sort(pp.begin(), pp.end(), [](const PP& u, const PP& v) { return std::fabs(u.ucc) > std::fabs(v.ucc); });
+      const int K = (int)pp.size();
+      int ke = 0;
+      while (ke < K && std::fabs(pp[ke].ucc) >= PC_PRIM_EPS) ++ke;
+      p.keff = std::max(ke, 1);
+      double* o = &h->prim_host[p.prim_off * 6];
+      for (int q = 0; q < K; ++q, o += 6) {
+        o[0] = pp[q].sigma; o[1] = pp[q].ucc;
+        o[2] = pp[q].P[0];  o[3] = pp[q].P[1];
+        o[4] = pp[q].P[2];  o[5] = pp[q].kz;
+      }
+    }
+  });
+}
+
+// (re)build and upload the SoA tables of one bucket in its current pair order
+int upload_kind(pc_basis* h, Kind* k) {
+  const int n = (int)k->pairs.size();
+  const int K = k->K;
+  std::vector<int> fx(n), fy(n), pid(n), keff(n);
+  std::vector<double> xy((size_t)3 * n), prim((size_t)6 * K * n);
   for (int i = 0; i < n; ++i) {
     const HostPair& p = h->pairs[k->pairs[i]];
     const Shell& X = h->shells[p.x];
@@ -546,43 +618,17 @@ int upload_kind(pc_basis* h, Kind* k) {
     fx[i] = X.first_fn;
     fy[i] = Y.first_fn;
     pid[i] = k->pairs[i];
-    double r2 = 0;
-    for (int c = 0; c < 3; ++c) {
-      const double d = X.A[c] - Y.A[c];
-      xy[(size_t)c * n + i] = d;
-      r2 += d * d;
-    }
-    const double cn = lnorm[X.l] * lnorm[Y.l] * pf_half;
-    // primitive pairs of this shell pair, most significant first.  Pairs whose prefactor
-    // U*cc is below PC_PRIM_EPS contribute < 1e-20 to any integral (two-centre pairs of tight
-    // primitives: U = exp(-ab/(a+b) r^2) underflows) and are cut off by keff.  The reference
-    // visits them all (no primitive screening); the results differ by < 1e-16.
-    struct PP { double sigma, ucc, P[3], kz; };
-    std::vector<PP> pp;
-    pp.reserve(K);
-    for (int ia = 0; ia < X.K; ++ia)
-      for (int ib = 0; ib < Y.K; ++ib) {
-        const double a = h->exps[X.poff + ia], b = h->exps[Y.poff + ib];
-        PP e;
-        e.sigma = 1.0 / (a + b);
-        const double U = std::pow(M_PI * e.sigma, 1.5) * std::exp(-a * b * e.sigma * r2);
-        e.ucc = U * h->scc[X.poff + ia] * h->scc[Y.poff + ib] * cn;
-        for (int c = 0; c < 3; ++c) e.P[c] = (a * X.A[c] + b * Y.A[c]) * e.sigma;
-        e.kz = b * e.sigma;  // kappa*zeta = (2b)(sigma/2)
-        pp.push_back(e);
-      }
-    std::stable_sort(pp.begin(), pp.end(), [](const PP& u, const PP& v) { return std::fabs(u.ucc) > std::fabs(v.ucc); });
-    int ke = 0;
-    while (ke < K && std::fabs(pp[ke].ucc) >= PC_PRIM_EPS) ++ke;
-    keff[i] = std::max(ke, 1);
-    for (int q = 0; q < K; ++q) {
+    for (int c = 0; c < 3; ++c) xy[(size_t)c * n + i] = X.A[c] - Y.A[c];
+    keff[i] = p.keff;
+    const double* src = &h->prim_host[p.prim_off * 6];
+    for (int q = 0; q < K; ++q, src += 6) {
       // [K][3][n] double2: {sigma, U}, {Px, Py}, {Pz, kz}: three 16-byte loads per primitive pair
       double* o0 = &prim[(((size_t)q * 3 + 0) * n + i) * 2];
       double* o1 = &prim[(((size_t)q * 3 + 1) * n + i) * 2];
       double* o2 = &prim[(((size_t)q * 3 + 2) * n + i) * 2];
-      o0[0] = pp[q].sigma; o0[1] = pp[q].ucc;
-      o1[0] = pp[q].P[0];  o1[1] = pp[q].P[1];
-      o2[0] = pp[q].P[2];  o2[1] = pp[q].kz;
+      o0[0] = src[0]; o0[1] = src[1];
+      o1[0] = src[2]; o1[1] = src[3];
+      o2[0] = src[4]; o2[1] = src[5];
     }
   }
   k->keff_h = keff;
@@ -919,6 +965,7 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
       h->kinds[p.kind]->pairs.push_back((int)h->pairs.size());
       h->pairs.push_back(p);
     }
+  compute_pair_prims(h);
   for (Kind* k : h->kinds)
     if (upload_kind(h, k)) { delete h; return 1; }
   {
@@ -1121,16 +1168,6 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       const Kind* Kt = h->kinds[w.kk];
       build_segments_host(B->pm, B->gstart, B->keff_h, Kt->pm, Kt->gstart, Kt->keff_h, w.same, w.run, thresh,
                           w.seg_off, w.seg_q, w.seg_prim, w.ij);
-    };
-    auto parallel_for = [&](size_t n, const std::function<void(size_t)>& fn) {
-      const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-      std::atomic<size_t> next(0);
-      std::vector<std::thread> pool;
-      for (unsigned t = 0; t < hw; ++t)
-        pool.emplace_back([&]() {
-          for (size_t k = next.fetch_add(1); k < n; k = next.fetch_add(1)) fn(k);
-        });
-      for (auto& th : pool) th.join();
     };
     parallel_for(work.size(), [&](size_t k) { build_segments(work[k]); });
     // ---- phase B: plan items + static multi-GPU schedule ---------------------
