@@ -63,7 +63,7 @@ def build(verbose=False, jobs=None):
     srcs = [os.path.join(CSRC, "pc_api.cu"), os.path.join(CSRC, "pc_mp2.cu"), os.path.join(CSRC, "pc_generic.cu")] + sorted(
         os.path.join(GEN, f) for f in os.listdir(GEN) if f.endswith(".cu"))
     api_deps = deps + [os.path.join(HERE, "..", "include", "pychem_b200.h"), os.path.join(CSRC, "pc_one_electron.cuh"),
-                       os.path.join(CSRC, "pc_generic_class.h")]
+                       os.path.join(CSRC, "pc_generic_class.h"), os.path.join(CSRC, "pc_jk_kernels.cuh")]
     # biggest files first so the pool stays busy
     srcs.sort(key=lambda p: -os.path.getsize(p))
     jobs = jobs or min(8, os.cpu_count() or 1)

@@ -112,7 +112,7 @@ def build(jobs=None, regenerate=True):
         with contextlib.redirect_stdout(io.StringIO()):
             gen_eri.main(GEN)
     csrc_out = os.path.join(SRC, "pychem_b200", "csrc")
-    headers = ["pc_common.cuh", "pc_one_electron.cuh", "pc_generic.cuh", "pc_generic_class.h"]
+    headers = ["pc_common.cuh", "pc_one_electron.cuh", "pc_generic.cuh", "pc_generic_class.h", "pc_jk_kernels.cuh"]
     dep = hashlib.sha1()
     for hname in headers:
         t = transform(open(os.path.join(CSRC, hname)).read(), hname)
