@@ -324,3 +324,15 @@ def test_emu_f_shell_dropin_scf(emu, gold, monkeypatch, tmp_path):
         undo()
         hf_gpu.release()
         ints_gpu.release()
+
+
+def test_emu_unsupported_shells_are_refused_loudly(emu):
+    """g shells and Cartesian f shells: pc_basis_create fails with a message, no silent fallback."""
+    import copy
+    tb = emu.EmuBasis(helpers.molecule("hf_tz")).table
+    for mutate, word in ((lambda t: t.l.__setitem__(9, 4), "s, p, d, f"), (lambda t: t.is_cart.__setitem__(9, 1), "Cartesian f")):
+        bad = copy.deepcopy(tb)
+        mutate(bad)
+        with pytest.raises(emu.EmuError) as err:
+            emu.EmuBasis(bad)
+        assert word in str(err.value)
