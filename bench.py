@@ -426,6 +426,12 @@ def run_b200(args):
                                "algorithmic_gflop_per_step": all_flops / 1e9,
                                "reference_unscreened_gflop_per_step": ref_flops / 1e9,
                                "serialised_kernel_ms_over_step_ms": eri_ms / ms_step if ms_step else None},
+                "fp64_instruction_bound": {
+                    "dominant_kernel_frac_ceiling": 0.407 if top[0] == "psss" else None,
+                    "whole_step_frac_ceiling": 0.707,
+                    "note": "static SASS count of the built kernels (tools/sass_mix.py, profiles/r1d_sass_instruction_mix.txt): "
+                            "FP64-pipe instructions actually executed per primitive quartet vs the flop model above -- the "
+                            "share of the FP64 peak a perfectly pipelined loop of the present code could show under that model"},
                 "flop_count": "executed primitive quartets (after the 1e-24 primitive-pair cut-off) * flop_prim "
                               "+ quartets * (flop_cont + digestion), SURVEY 8(d) model on the generator's DAG "
                               "(pychem_b200/data/flop_model.json)"}
