@@ -83,6 +83,7 @@ def test_batched_jk_full_size_stored_equals_direct():
         _lib.check(db.lib.pc_jk_direct_batch_accumulate(db.h, 5, engine._ptr(D), engine._ptr(acc)))
         torch.cuda.synchronize()
         total += acc
+    torch.cuda.synchronize()          # `total` is summed on torch's stream, finalised on the library's
     out = np.empty_like(D)
     _lib.check(db.lib.pc_jk_finalize_batch(db.h, 5, engine._ptr(total), engine._ptr(out)))
     assert np.abs(out - direct).max() < 1e-10 * scale
