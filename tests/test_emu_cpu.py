@@ -308,7 +308,7 @@ def test_emu_f_shell_dropin_scf(emu, gold, monkeypatch, tmp_path):
     from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu
     monkeypatch.setattr(ints_gpu, "DeviceBasis", emu.EmuDeviceBasis)
     ns = ref_driver.modules()
-    undo = hf_gpu.install(ns.hartree_fock)
+    undo = hf_gpu.install(ns.hartree_fock, one_electron=True)      # Core/Overlap from one_electron_kernel<3> too
     try:
         inp = str(tmp_path / "hf.inp")
         ref_driver.write_input(inp, "hf", helpers.HYDROGEN_FLUORIDE, "cc-pVTZ")

@@ -164,7 +164,7 @@ def test_f_shell_dropin_scf(gold, tmp_path):
         pytest.skip("oracle/_ref (reference copy) not shipped")
     from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu
     ns = ref_driver.modules()
-    undo = hf_gpu.install(ns.hartree_fock)
+    undo = hf_gpu.install(ns.hartree_fock, one_electron=True)      # Core/Overlap from one_electron_kernel<3> too
     try:
         inp = str(tmp_path / "hf.inp")
         ref_driver.write_input(inp, "hf", helpers.HYDROGEN_FLUORIDE, "cc-pVTZ")
