@@ -15,6 +15,7 @@ Fixtures:
   h2o2_631gss.npz  (H2O)2 6-31G**           : sampled shell quartets covering all 21 l<=2
                                               classes on four distinct centres
   benzene_631gs.npz benzene 6-31G*          : sampled shell quartets
+  h2o_631gss_cartd.npz H2O 6-31G**, Cartesian_L = [2]: full tensor, SCF energy
   h3_sto3g_mp2.npz Tests/example1.inp       : HF and HF+MP2 total energies
 """
 import os
@@ -104,6 +105,18 @@ def sample_quartets(ns, mol, per_class, seed, max_tries=200000):
         blocks.append(np.asarray(blk).ravel().copy())
     offs = np.concatenate([[0], np.cumsum([len(x) for x in blocks])])
     return np.array(quartets, dtype=np.int32), np.concatenate(blocks), offs.astype(np.int64), got
+
+
+def mint_cartesian_d(ns, path=None):
+    """h2o_631gss_cartd.npz: the reference's Cartesian_L keyword (Util/structures.py:844-849), RHF
+    on H2O 6-31G** with six Cartesian d functions: dense tensor and SCF energy."""
+    inp = os.path.join(GOLD, "_h2o_cartd.inp")
+    ref_driver.write_input(inp, "h2o", S.H2O_MONOMER, "6-31G**", extra="Cartesian_L = [2]")
+    mol = ref_driver.run(inp)
+    os.remove(inp)
+    np.savez_compressed(path or os.path.join(GOLD, "h2o_631gss_cartd.npz"),
+                        G=np.asarray(mol.CoulombIntegrals, dtype=np.float64), energy=mol.States[0].TotalEnergy)
+    print("H2O Cartesian d", mol.NOrbitals, repr(mol.States[0].TotalEnergy))
 
 
 def main():
@@ -201,6 +214,9 @@ def main():
         one_e[name + "_overlap"] = np.array(mol.Overlap)
         print("one-electron", name, mol.NOrbitals, np.trace(mol.Core), np.trace(mol.Overlap))
     np.savez_compressed(os.path.join(GOLD, "one_electron.npz"), **one_e)
+
+    # ---------------- H2O 6-31G** with Cartesian d functions (Cartesian_L = [2]) ---------
+    mint_cartesian_d(ns)
 
     # ---------------- H2O 6-31G** RHF + MP2 (reference mp2.do, O(N^6) Python) -----------
     inp = os.path.join(GOLD, "_h2o_mp2.inp")
