@@ -6,7 +6,7 @@ no /root/reference, so the (public, EMSL-derived) numbers for the handful of set
 BASELINE configs use are written once to pychem_b200/data/basis_subset.json in the reference's
 own record format ``[l, [exponent, coefficient], ...]`` (Util/structures.py:836-843).
 
-Usage: python tools/extract_basis.py   (needs oracle/_ref built, i.e. /root/reference present)
+Usage: python oracle/extract_basis.py   (needs oracle/_ref built, i.e. /root/reference present)
 """
 import json
 import os

@@ -2,7 +2,7 @@
 """CPU-baseline numbers of the REFERENCE itself on this host (SURVEY 8(d) "CPU baseline beside
 it"): evaluate_2e_ints wall time and make_coulomb_exchange_matrices ms/call for the small
 BASELINE configs, 1 core (the reference is single-threaded).  Test/measurement infrastructure:
-drives oracle/_ref.  Usage: python tools/ref_cpu_numbers.py > profiles/...json"""
+drives oracle/_ref.  Usage: python oracle/ref_cpu_numbers.py > profiles/...json"""
 import json
 import os
 import platform

@@ -32,7 +32,7 @@ _BASIS_CACHE = None
 
 
 def basis_library():
-    """The shipped subset of basis-set data (tools/extract_basis.py)."""
+    """The shipped subset of basis-set data (written once in the authoring container from the reference's Data/basis.py)."""
     global _BASIS_CACHE
     if _BASIS_CACHE is None:
         path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "basis_subset.json")
@@ -88,7 +88,7 @@ class Atom:
         lib = basis_library()
         if basis_set not in lib or self.Label not in lib[basis_set]:
             raise KeyError("basis %s / element %s is not in pychem_b200/data/basis_subset.json "
-                           "(extend tools/extract_basis.py)" % (basis_set, self.Label))
+                           "(extend the element / basis lists of the extraction script and rerun it)" % (basis_set, self.Label))
         self.Basis = [ContractedGaussian(f, cartesian_l) for f in lib[basis_set][self.Label]
                       if max_l is None or f[0] <= max_l]
         self.NFunctions = sum(c.NAngMom for c in self.Basis)

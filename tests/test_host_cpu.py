@@ -46,6 +46,12 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("oracle/", "").lower() or f in ("build.py",), f
+    # only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline leg may execute anything under
+    # oracle/: the developer tools that need the reference or the oracle live under oracle/ themselves
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert "from oracle" not in text and "import oracle" not in text and "oracle/_ref" not in text, f
 
 
 def test_basis_table_matches_reference_layout():
