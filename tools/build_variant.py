@@ -32,8 +32,9 @@ def main():
     csrc = os.path.join(work, "pychem_b200", "csrc")
     os.makedirs(os.path.join(csrc, "gen"), exist_ok=True)
     os.makedirs(os.path.join(work, "include"), exist_ok=True)
-    for f in ("pc_api.cu", "pc_mp2.cu", "pc_common.cuh", "pc_one_electron.cuh"):
-        shutil.copy(os.path.join(PKG, "csrc", f), os.path.join(csrc, f))
+    for f in os.listdir(os.path.join(PKG, "csrc")):
+        if f.endswith((".cu", ".cuh", ".h")):
+            shutil.copy(os.path.join(PKG, "csrc", f), os.path.join(csrc, f))
     shutil.copy(os.path.join(ROOT, "include", "pychem_b200.h"), os.path.join(work, "include", "pychem_b200.h"))
     sys.path.insert(0, os.path.join(PKG, "codegen"))
     import contextlib
@@ -60,7 +61,7 @@ def main():
     os.makedirs(objdir, exist_ok=True)
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
              "-diag-suppress", "177", "-diag-suppress", "550"]
-    srcs = [os.path.join(csrc, "pc_api.cu"), os.path.join(csrc, "pc_mp2.cu")] + sorted(
+    srcs = [os.path.join(csrc, "pc_api.cu"), os.path.join(csrc, "pc_mp2.cu"), os.path.join(csrc, "pc_generic.cu")] + sorted(
         os.path.join(csrc, "gen", f) for f in os.listdir(os.path.join(csrc, "gen")) if f.endswith(".cu"))
     srcs.sort(key=lambda p: -os.path.getsize(p))
 
