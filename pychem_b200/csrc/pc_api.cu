@@ -120,9 +120,10 @@ struct PlanItem {
   long long total_q, count_q;  // quartets of the bucket pair / of this rank's slice
   double prim_exec;        // primitive quartets actually visited by the whole bucket pair
   int nseg;
-  DevBuf<long long>* seg_off;
-  DevBuf<int>* seg_ij;     // int2 per segment
-  DevBuf<int>* warp_s0;
+  // device tables of the item: views into the plan's three pooled buffers (pc_basis::plan_*)
+  const long long* seg_off;
+  const int* seg_ij;       // int2 per segment
+  const int* warp_s0;
 };
 
 // the bucket pairs of one angular-momentum class that go into one fused kernel launch
@@ -218,8 +219,10 @@ struct pc_basis {
   int rank = 0, nranks = 1;
   std::vector<PlanItem> plan;
   std::vector<LaunchGroup> groups;     // launch order (longest first)
-  std::vector<DevBuf<long long>*> plan_bufs;
-  std::vector<DevBuf<int>*> plan_ibufs;
+  // segment tables of ALL plan items, one allocation and one upload each (hundreds of bucket
+  // pairs: per-item buffers cost more in cudaMalloc than the plan costs to build)
+  DevBuf<long long> plan_seg_off;
+  DevBuf<int> plan_seg_ij, plan_warp_s0;
   long long my_quartets = 0, my_eris = 0, all_quartets = 0, all_eris = 0;
   // scratch
   DevBuf<double> acc, dstage, ostage;
@@ -261,8 +264,6 @@ struct pc_basis {
     if (ev_fork) cudaEventDestroy(ev_fork);
     for (auto st : side) cudaStreamDestroy(st);
     for (auto* k : kinds) delete k;
-    for (auto* b : plan_bufs) delete b;
-    for (auto* b : plan_ibufs) delete b;
     for (auto* b : gen_bufs) delete b;
     if (stream) cudaStreamDestroy(stream);
   }
@@ -511,7 +512,7 @@ int launch_group(pc_basis* h, int mode, const LaunchGroup& g, PcEriArgs& A, cuda
     if (it.count == 0) continue;
     PcItem& I = A.items[n++];
     fill_item(I, h->kinds[it.kb], h->kinds[it.kk]);
-    I.seg_off = it.seg_off->p; I.seg_ij = (const int2*)it.seg_ij->p; I.warp_s0 = it.warp_s0->p;
+    I.seg_off = it.seg_off; I.seg_ij = (const int2*)it.seg_ij; I.warp_s0 = it.warp_s0;
     I.nseg = it.nseg; I.t_begin = it.begin; I.t_count = it.count;
     I.same = it.same;
     I.warp0 = warp;
@@ -880,10 +881,6 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
   if (!h->schwarz_done && pc_schwarz(h, nullptr, nullptr)) return 1;
   PC_CUDA(cudaSetDevice(h->device));
   if (!(h->planned && h->thresh == thresh && h->rank == rank && h->nranks == nranks)) {
-    for (auto* b : h->plan_bufs) delete b;
-    h->plan_bufs.clear();
-    for (auto* b : h->plan_ibufs) delete b;
-    h->plan_ibufs.clear();
     for (auto* b : h->gen_bufs) delete b;
     h->gen_bufs.clear();
     h->plan.clear();
@@ -979,22 +976,32 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         w.s0[(size_t)wi] = cur;
       }
     });
-    // ---- phase D: uploads (one synchronisation at the end) ---------------------------------
+    // ---- phase D: uploads into the three pooled buffers (one synchronisation at the end) ----
+    {
+      size_t n_off = 0, n_ij = 0, n_s0 = 0;
+      for (size_t k = 0; k < h->plan.size(); ++k) {
+        if (h->plan[k].count == 0) continue;
+        const Work& w = work[widx[k]];
+        n_off += w.seg_off.size(); n_ij += w.ij.size(); n_s0 += w.s0.size();
+      }
+      PC_CUDA(h->plan_seg_off.alloc(n_off));
+      PC_CUDA(h->plan_seg_ij.alloc(n_ij));
+      PC_CUDA(h->plan_warp_s0.alloc(n_s0));
+    }
+    size_t o_off = 0, o_ij = 0, o_s0 = 0;       // w.ij holds int2 records: every item starts 8-byte aligned
     for (size_t k = 0; k < h->plan.size(); ++k) {
       PlanItem& it = h->plan[k];
       const Work& w = work[widx[k]];
       const Kind* B = h->kinds[it.kb];
       const Kind* Kt = h->kinds[it.kk];
-      it.seg_off = new DevBuf<long long>();
-      h->plan_bufs.push_back(it.seg_off);
-      it.seg_ij = new DevBuf<int>();
-      it.warp_s0 = new DevBuf<int>();
-      h->plan_ibufs.push_back(it.seg_ij);
-      h->plan_ibufs.push_back(it.warp_s0);
       if (it.count > 0) {
-        PC_CUDA(it.seg_off->upload(w.seg_off, h->stream));
-        PC_CUDA(it.seg_ij->upload(w.ij, h->stream));
-        PC_CUDA(it.warp_s0->upload(w.s0, h->stream));
+        it.seg_off = h->plan_seg_off.p + o_off;
+        it.seg_ij = h->plan_seg_ij.p + o_ij;
+        it.warp_s0 = h->plan_warp_s0.p + o_s0;
+        PC_CUDA(cudaMemcpyAsync(h->plan_seg_off.p + o_off, w.seg_off.data(), w.seg_off.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+        PC_CUDA(cudaMemcpyAsync(h->plan_seg_ij.p + o_ij, w.ij.data(), w.ij.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        PC_CUDA(cudaMemcpyAsync(h->plan_warp_s0.p + o_s0, w.s0.data(), w.s0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        o_off += w.seg_off.size(); o_ij += w.ij.size(); o_s0 += w.s0.size();
       }
       const long long nsph = (long long)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);
       h->all_quartets += it.total_q; h->all_eris += it.total_q * nsph;
