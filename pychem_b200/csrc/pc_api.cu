@@ -49,7 +49,9 @@ struct DevBuf {
     return cudaMalloc((void**)&p, count * sizeof(T));
   }
   cudaError_t upload(const std::vector<T>& v, cudaStream_t st) {
-    cudaError_t e = alloc(v.size());
+    // same size as before (tables rebuilt in a new order): keep the allocation, the copy is
+    // ordered after earlier work on the stream
+    cudaError_t e = (p && n == v.size()) ? cudaSuccess : alloc(v.size());
     if (e != cudaSuccess || v.empty()) return e;
     return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st);
   }
