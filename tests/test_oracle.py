@@ -173,3 +173,23 @@ def test_f_shell_md_yardstick_matches_reference_live():
     with np.errstate(all="ignore"):
         md = md_eri.shell_quartet([shells[s] for s in q], transform_basis.cart_to_spher)
     assert np.abs(md - ref).max() < ERI_TOL
+
+
+def test_f_shell_scattering_matches_reference_live():
+    """ints_type = 1 with f shells (Bessel orders up to 12): the restatement against the live
+    reference on quartets without a goofy (d f) pair (needs oracle/_ref)."""
+    if not ref_driver.available():
+        pytest.skip("oracle/_ref not built")
+    ns = ref_driver.modules()
+    mol, _ = ref_driver.build_molecule(helpers.CNON, "cc-pVTZ")
+    ob = oracle.OracleBasis(BasisTable(helpers.molecule("cnon_tz")))
+    quartets = [(9, 19, 3, 13), (9, 9, 19, 19), (9, 29, 19, 39), (6, 19, 9, 13), (9, 19, 4, 29), (3, 9, 13, 39)]
+    try:
+        for S in (0.0, 0.5, 2.0, 7.5):
+            oracle.set_ints_type(1, S)
+            for q in quartets:
+                with np.errstate(all="ignore"):
+                    ref = np.asarray(ns.integrals.two_electron(mol.ShellPairs[q[:2]], mol.ShellPairs[q[2:]], 1, S))
+                assert np.abs(ref - ob.quartet(*q)).max() < ERI_TOL, (S, q)
+    finally:
+        oracle.set_ints_type(0, -1.0)
