@@ -622,3 +622,145 @@ void orc_jk(int N, const double *G, const double *Dt, const double *Da, const do
         J[a * n + b] += j;
       }
 }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Sampled J blocks and X rows for molecules whose N^4 tensor cannot be stored ((H2O)16/32).   */
+/* Same semantics as orc_eri_tensor + orc_jk restricted to the requested outputs: a block      */
+/* (ab|cd) of the reference's tensor is non-zero iff (ab) == (cd) or max(B_ab) max(B_cd) >     */
+/* thresh (hartree_fock.py:244-250, 293-294; the 8-fold scatter :314-325 makes that symmetric  */
+/* in all index permutations), and                                                             */
+/*   J[m,n]  =  sum_{l,s} Dt[l,s] G[m,n,l,s]       for (m,n) in the listed shell pairs  (:345)  */
+/*   X[m,s]  = -sum_{n,l} D[l,n]  G[m,n,l,s]       for m in the listed shells, all s    (:346)  */
+/* J, Xa, Xb are N x N, zeroed here; only the sampled blocks / rows are filled (J also at the  */
+/* transposed position).  pmax: Schwarz maxima from orc_schwarz.  Ket pairs are spread over    */
+/* `nthreads` POSIX threads (the reference is single-threaded; this is only the checker).      */
+/* ------------------------------------------------------------------------------------------ */
+#include <pthread.h>
+
+typedef struct {
+  const orc_basis *bs;
+  double thresh;
+  const double *pmax, *Dt, *Da, *Db;
+  int a, b, is_k;            /* J block (a,b) or X rows of shell a */
+  volatile int *next;        /* shared counter over the first ket shell c */
+  pthread_mutex_t *mu;
+  double *jblk;              /* [49] shared */
+  double *xa, *xb;           /* [7][N] shared */
+  long *nq;
+} orc_job;
+
+static void *orc_sample_worker(void *arg) {
+  orc_job *jb = (orc_job *)arg;
+  const orc_basis *bs = jb->bs;
+  const int n = bs->nshell, a = jb->a;
+  const size_t N = bs->nbf;
+  const orc_shell *A = &bs->sh[a];
+  double loc[49], *blk = (double *)malloc(sizeof(double) * 49 * 49);
+  double *ra = NULL, *rb = NULL;
+  long my = 0;
+  memset(loc, 0, sizeof(loc));
+  if (jb->is_k) { ra = (double *)calloc(7 * N, sizeof(double)); rb = (double *)calloc(7 * N, sizeof(double)); }
+  for (;;) {
+    const int c = __sync_fetch_and_add(jb->next, 1);
+    if (c >= n) break;
+    for (int d = c; d < n; d++) {
+      const size_t pcd = pair_index(n, c, d);
+      const orc_shell *C = &bs->sh[c], *D = &bs->sh[d];
+      if (!jb->is_k) {
+        const int b = jb->b;
+        const orc_shell *B = &bs->sh[b];
+        const size_t pab = pair_index(n, a < b ? a : b, a < b ? b : a);
+        if (!(pcd == pab || jb->pmax[pab] * jb->pmax[pcd] > jb->thresh)) continue;
+        orc_eri_quartet(bs, a, b, c, d, blk);
+        my++;
+        for (int m = 0; m < A->nfn; m++) for (int q = 0; q < B->nfn; q++) {
+          double s = 0;
+          for (int l = 0; l < C->nfn; l++) for (int r = 0; r < D->nfn; r++) {
+            const double g = blk[(((size_t)m * B->nfn + q) * C->nfn + l) * D->nfn + r];
+            double dd = jb->Dt[(C->first_fn + l) * N + D->first_fn + r];
+            if (c != d) dd += jb->Dt[(D->first_fn + r) * N + C->first_fn + l];
+            s += dd * g;
+          }
+          loc[m * B->nfn + q] += s;
+        }
+      } else {
+        for (int b = 0; b < n; b++) {
+          const size_t pab = pair_index(n, a < b ? a : b, a < b ? b : a);
+          if (!(pcd == pab || jb->pmax[pab] * jb->pmax[pcd] > jb->thresh)) continue;
+          const orc_shell *B = &bs->sh[b];
+          orc_eri_quartet(bs, a, b, c, d, blk);
+          my++;
+          for (int m = 0; m < A->nfn; m++) for (int q = 0; q < B->nfn; q++)
+            for (int l = 0; l < C->nfn; l++) for (int r = 0; r < D->nfn; r++) {
+              const double g = blk[(((size_t)m * B->nfn + q) * C->nfn + l) * D->nfn + r];
+              const size_t fb = B->first_fn + q, fc = C->first_fn + l, fd = D->first_fn + r;
+              /* (m b | c d): X[m,d] -= D[c,b] g ; its image (m b | d c): X[m,c] -= D[d,b] g */
+              ra[m * N + fd] -= jb->Da[fc * N + fb] * g;
+              rb[m * N + fd] -= jb->Db[fc * N + fb] * g;
+              if (c != d) {
+                ra[m * N + fc] -= jb->Da[fd * N + fb] * g;
+                rb[m * N + fc] -= jb->Db[fd * N + fb] * g;
+              }
+            }
+        }
+      }
+    }
+  }
+  pthread_mutex_lock(jb->mu);
+  if (!jb->is_k) {
+    for (int k = 0; k < 49; k++) jb->jblk[k] += loc[k];
+  } else {
+    for (size_t k = 0; k < (size_t)A->nfn * N; k++) { jb->xa[k] += ra[k]; jb->xb[k] += rb[k]; }
+  }
+  *jb->nq += my;
+  pthread_mutex_unlock(jb->mu);
+  free(blk); free(ra); free(rb);
+  return NULL;
+}
+
+void orc_jk_sample(const orc_basis *bs, double thresh, const double *pmax, int nJ, const int *jab,
+                   int nK, const int *ka, const double *Dt, const double *Da, const double *Db,
+                   double *J, double *Xa, double *Xb, int nthreads, long *nquartets) {
+  const size_t N = bs->nbf;
+  memset(J, 0, sizeof(double) * N * N);
+  memset(Xa, 0, sizeof(double) * N * N);
+  memset(Xb, 0, sizeof(double) * N * N);
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 64) nthreads = 64;
+  long nq = 0;
+  pthread_mutex_t mu;
+  pthread_mutex_init(&mu, NULL);
+  double *xa = (double *)malloc(sizeof(double) * 7 * N), *xb = (double *)malloc(sizeof(double) * 7 * N);
+  for (int t = 0; t < nJ + nK; t++) {
+    double jblk[49];
+    volatile int next = 0;
+    orc_job jb;
+    memset(jblk, 0, sizeof(jblk));
+    memset(xa, 0, sizeof(double) * 7 * N);
+    memset(xb, 0, sizeof(double) * 7 * N);
+    jb.bs = bs; jb.thresh = thresh; jb.pmax = pmax; jb.Dt = Dt; jb.Da = Da; jb.Db = Db;
+    jb.is_k = t >= nJ;
+    jb.a = jb.is_k ? ka[t - nJ] : jab[2 * t];
+    jb.b = jb.is_k ? 0 : jab[2 * t + 1];
+    jb.next = &next; jb.mu = &mu; jb.jblk = jblk; jb.xa = xa; jb.xb = xb; jb.nq = &nq;
+    pthread_t th[64];
+    for (int k = 0; k < nthreads; k++) pthread_create(&th[k], NULL, orc_sample_worker, &jb);
+    for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    const orc_shell *A = &bs->sh[jb.a];
+    if (!jb.is_k) {
+      const orc_shell *B = &bs->sh[jb.b];
+      for (int m = 0; m < A->nfn; m++) for (int q = 0; q < B->nfn; q++) {
+        J[(A->first_fn + m) * N + B->first_fn + q] = jblk[m * B->nfn + q];
+        J[(B->first_fn + q) * N + A->first_fn + m] = jblk[m * B->nfn + q];
+      }
+    } else {
+      for (int m = 0; m < A->nfn; m++) for (size_t s = 0; s < N; s++) {
+        Xa[(A->first_fn + m) * N + s] = xa[m * N + s];
+        Xb[(A->first_fn + m) * N + s] = xb[m * N + s];
+      }
+    }
+  }
+  free(xa); free(xb);
+  pthread_mutex_destroy(&mu);
+  if (nquartets) *nquartets = nq;
+}

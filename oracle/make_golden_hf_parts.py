@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Mint tests/golden/hf_ccpvtz_parts.npz: the pieces of the hydrogen-fluoride / cc-pVTZ RHF job
+(the f-shell drop-in case) from the REAL reference (oracle/_ref, HRR stride corrected as in
+oracle/make_golden_f.py), so that a deviation of the drop-in energy can be bisected quantity by
+quantity on the device.
+
+TEST INFRASTRUCTURE ONLY.  Stored: Core, Overlap (hartree_fock.make_core_matrices), the
+orthogonaliser X, the converged alpha density, J / X_alpha built from it with the reference's
+einsum (hartree_fock.py:345-347), the nuclear repulsion and the total energy.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import make_golden_f, ref_driver  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+class _M:
+    pass
+
+
+def main():
+    ns = ref_driver.modules()
+    fixed = make_golden_f.compile_fixed_c_ints()
+    stock = ns.integrals._c_ints
+    ns.integrals._c_ints = fixed
+    try:
+        inp = os.path.join(GOLD, "_hf.inp")
+        ref_driver.write_input(inp, "hf", make_golden_f.HYDROGEN_FLUORIDE, "cc-pVTZ")
+        mol = ref_driver.run(inp)
+        os.remove(inp)
+    finally:
+        ns.integrals._c_ints = stock
+    st = mol.States[0]
+    this = _M()
+    this.Total, this.Alpha, this.Beta = _M(), _M(), _M()
+    this.Total.Density = np.array(st.Total.Density)
+    this.Alpha.Density = np.array(st.Alpha.Density)
+    this.Beta.Density = np.array(st.Beta.Density)
+    ns.hartree_fock.make_coulomb_exchange_matrices(mol, this)
+    out = dict(core=np.array(mol.Core), overlap=np.array(mol.Overlap), X=np.array(mol.X),
+               Dt=this.Total.Density, Da=this.Alpha.Density, J=np.array(this.Total.Coulomb),
+               Xa=np.array(this.Alpha.Exchange), energy=st.TotalEnergy,
+               nuclear_repulsion=getattr(mol, "NuclearRepulsion", np.nan))
+    np.savez_compressed(os.path.join(GOLD, "hf_ccpvtz_parts.npz"), **out)
+    print("wrote hf_ccpvtz_parts.npz; E =", repr(st.TotalEnergy), "core range", out["core"].min(), out["core"].max())
+
+
+if __name__ == "__main__":
+    main()

@@ -37,6 +37,8 @@ def lib():
         L.orc_eri_tensor.argtypes = [ctypes.c_void_p, ctypes.c_double, c_dp]
         L.orc_jk.argtypes = [ctypes.c_int] + [c_dp] * 7
         L.orc_set_ints_type.argtypes = [ctypes.c_int, ctypes.c_double]
+        L.orc_jk_sample.argtypes = [ctypes.c_void_p, ctypes.c_double, c_dp, ctypes.c_int, c_ip, ctypes.c_int, c_ip,
+                                    c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, ctypes.c_int, ctypes.POINTER(ctypes.c_long)]
         L.orc_boys_coeff.restype = ctypes.c_double
         L.orc_boys_coeff.argtypes = [ctypes.c_int] * 3
         _LIB = L
@@ -92,6 +94,34 @@ class OracleBasis:
         G = np.zeros((N, N, N, N))
         nsurv = self.L.orc_eri_tensor(self.h, thresh, _dp(G))
         return G, nsurv
+
+
+def jk_sample(ob, Dt, Da, Db, j_pairs, k_shells, thresh=1.0e-8, pmax=None, nthreads=None):
+    """Sampled J blocks (shell pairs `j_pairs`) and X rows (shells `k_shells`) of
+    make_coulomb_exchange_matrices for molecules whose N^4 tensor cannot be stored.  Returns
+    (J, Xa, Xb, mask_J, mask_X, nquartets): N x N arrays holding the sampled entries, boolean
+    masks of the entries that are filled."""
+    N = ob.nbf
+    if pmax is None:
+        _, pmax = ob.schwarz()
+    pmax = np.ascontiguousarray(pmax, dtype=float)
+    Dt, Da, Db = (np.ascontiguousarray(x, dtype=float) for x in (Dt, Da, Db))
+    jp = np.ascontiguousarray(np.asarray(j_pairs, dtype=np.int32).reshape(-1, 2))
+    ks = np.ascontiguousarray(np.asarray(k_shells, dtype=np.int32).ravel())
+    J, Xa, Xb = np.zeros((N, N)), np.zeros((N, N)), np.zeros((N, N))
+    nq = ctypes.c_long()
+    if nthreads is None:
+        nthreads = min(32, os.cpu_count() or 1)
+    ob.L.orc_jk_sample(ob.h, float(thresh), _dp(pmax), len(jp), _ip(jp), len(ks), _ip(ks), _dp(Dt), _dp(Da), _dp(Db),
+                       _dp(J), _dp(Xa), _dp(Xb), int(nthreads), ctypes.byref(nq))
+    mJ, mX = np.zeros((N, N), dtype=bool), np.zeros((N, N), dtype=bool)
+    f, nf = ob.t.first_fn, ob.t.nfn
+    for a, b in jp:
+        mJ[f[a]:f[a] + nf[a], f[b]:f[b] + nf[b]] = True
+        mJ[f[b]:f[b] + nf[b], f[a]:f[a] + nf[a]] = True
+    for a in ks:
+        mX[f[a]:f[a] + nf[a], :] = True
+    return J, Xa, Xb, mJ, mX, nq.value
 
 
 def jk(G, Dt, Da, Db):

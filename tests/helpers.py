@@ -57,3 +57,16 @@ def bounds_from_flat(table, flat):
             out[(a, b)] = flat[p, :na * nb].reshape(na, nb)
             p += 1
     return out
+
+
+def water_cluster_samples(n):
+    """Deterministic sample of outputs for the benchmark-size J/K parity checks on (H2O)_n
+    6-31G** (12 shells per water: O s s p s p d, H s s p, H s s p): eight shell pairs (a, b) whose
+    Coulomb blocks are compared and four shells whose exchange rows are compared, covering every
+    shell type, near and far pairs."""
+    w = lambda k, s: 12 * (k % n) + s          # noqa: E731  shell s of water k
+    j_pairs = [(w(0, 0), w(0, 0)), (w(0, 5), w(0, 5)), (w(0, 2), w(1, 4)), (w(0, 5), w(1, 7)),
+               (w(0, 3), w(5, 5)), (w(3, 8), w(3, 11)), (w(0, 4), w(n - 1, 4)), (w(7, 1), w(9, 5))]
+    j_pairs = [(min(a, b), max(a, b)) for a, b in j_pairs]
+    k_shells = [w(0, 5), w(0, 4), w(n // 2, 0), w(n - 1, 8)]
+    return j_pairs, k_shells

@@ -361,3 +361,27 @@ def test_emu_water_dimer_screened_direct_jk_vs_oracle(emu, monkeypatch, force_ge
         for mine, r in zip(db.jk_direct(a + b, a, b, variant=variant), ref):
             assert np.abs(mine - r).max() < JK_TOL * max(1.0, np.abs(r).max())
     db.close()
+
+
+def test_emu_direct_jk_vs_sampled_oracle_rows(emu):
+    """The benchmark-size GPU parity test (tests/test_gpu_zz_bench_size_parity.py) in small:
+    (H2O)3, integral-direct J/K of the emulated kernels against orc_jk_sample."""
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    n = 3
+    db = emu.EmuBasis(S.Molecule(S.water_cluster(n), "6-31G**"))
+    ob = oracle.OracleBasis(db.table)
+    _, pm0 = ob.schwarz()
+    db.plan(1.0e-8, 0, 1)
+    j_pairs, k_shells = helpers.water_cluster_samples(n)
+    rng = np.random.default_rng(103)
+    N = db.nbf
+    Da = _sym(rng, N)
+    A, B = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    for (Dt, D1, D2, variant) in ((2 * Da, Da, Da, emu.RHF), (A + B, A, B, emu.GEN)):
+        J0, Xa0, Xb0, mJ, mX, _ = oracle.jk_sample(ob, Dt, D1, D2, j_pairs, k_shells, pmax=pm0)
+        J, Xa, Xb = db.jk_direct(Dt, D1, D2, variant=variant)
+        assert np.abs(J - J0)[mJ].max() < JK_TOL
+        assert np.abs(Xa - Xa0)[mX].max() < JK_TOL
+        assert np.abs(Xb - Xb0)[mX].max() < JK_TOL
+    db.close()

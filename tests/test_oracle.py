@@ -193,3 +193,23 @@ def test_f_shell_scattering_matches_reference_live():
                 assert np.abs(ref - ob.quartet(*q)).max() < ERI_TOL, (S, q)
     finally:
         oracle.set_ints_type(0, -1.0)
+
+
+def test_sampled_jk_oracle_matches_full_tensor_oracle():
+    """orc_jk_sample (the checker of the benchmark-size GPU tests) against orc_eri_tensor + orc_jk
+    on (H2O)2, where N^4 can be stored: same screening, same contraction patterns."""
+    from oracle import oracle
+    from pychem_b200 import structures as S
+    from pychem_b200.basis_table import BasisTable
+    ob = oracle.OracleBasis(BasisTable(S.Molecule(S.water_cluster(2), "6-31G**")))
+    G, _ = ob.tensor(1.0e-8)
+    rng = np.random.default_rng(0)
+    N = ob.nbf
+    A, B = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    J0, Xa0, Xb0 = oracle.jk(G, A + B, A, B)
+    j_pairs, k_shells = helpers.water_cluster_samples(2)
+    J, Xa, Xb, mJ, mX, nq = oracle.jk_sample(ob, A + B, A, B, j_pairs, k_shells)
+    assert mJ.sum() > 0 and mX.sum() == N * sum(int(ob.t.nfn[s]) for s in set(k_shells))
+    assert np.abs(J - J0)[mJ].max() < 1e-12
+    assert np.abs(Xa - Xa0)[mX].max() < 1e-12
+    assert np.abs(Xb - Xb0)[mX].max() < 1e-12
