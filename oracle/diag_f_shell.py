@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""Bisect the hydrogen-fluoride / cc-pVTZ drop-in job quantity by quantity against the reference's
+"""TEST INFRASTRUCTURE ONLY (developer tool).  Bisect the hydrogen-fluoride / cc-pVTZ drop-in job quantity by quantity against the reference's
 own pieces (tests/golden/hf_ccpvtz_parts.npz, oracle/make_golden_hf_parts.py):
 Core, Overlap (one_electron_kernel<3>), J and X_alpha for the reference's converged density
 (stored and direct), and the energy expression evaluated with them.
 
-  python tools/diag_f_shell.py            # GPU (product library)
-  python tools/diag_f_shell.py --emu      # host emulation of the same kernels
+  python oracle/diag_f_shell.py            # GPU (product library)
+  python oracle/diag_f_shell.py --emu      # host emulation of the same kernels
 """
 import json
 import os
@@ -66,8 +66,29 @@ def main():
     e_mine = energy(np.asarray(core), np.asarray(J), np.asarray(Xa))
     print("electronic energy with the reference's density: mine - reference = %.3e" % (e_mine - e_ref))
     out["dE_fixed_density"] = float(e_mine - e_ref)
-    print("DIAG " + json.dumps(out))
     db.close()
+    # the drop-in SCF itself, Core/Overlap from the reference's own code or from the device
+    from oracle import ref_driver
+    if ref_driver.available() and not emu:
+        import tempfile
+        from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu
+        ns = ref_driver.modules()
+        for one_e in (False, True):
+            undo = hf_gpu.install(ns.hartree_fock, one_electron=one_e)
+            try:
+                inp = os.path.join(tempfile.mkdtemp(), "hf.inp")
+                ref_driver.write_input(inp, "hf", helpers.HYDROGEN_FLUORIDE, "cc-pVTZ")
+                m = ref_driver.run(inp)
+                e = float(m.States[0].TotalEnergy)
+                print("drop-in SCF one_electron=%s: E = %.14f  (E - reference = %.3e)" % (one_e, e, e - float(g["energy"])), flush=True)
+                out["scf_dE_one_electron_%s" % one_e] = e - float(g["energy"])
+                report("  SCF Core", np.asarray(m.Core), g["core"])
+                report("  SCF density", np.asarray(m.States[0].Alpha.Density), g["Da"])
+            finally:
+                undo()
+                hf_gpu.release()
+                ints_gpu.release()
+    print("DIAG " + json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -921,6 +921,11 @@ if os.environ.get("PC_GEN_RUN_CLASSES") is not None:
                        for kv in os.environ["PC_GEN_RUN_CLASSES"].split(",") if kv)
 
 
+# A/B variant builds (tools/build_variant.py) skip the Cartesian-d kernels: the dispatch table then
+# points at the spherical ones, which is wrong for Cartesian_L = [2] molecules and fine for timing
+SKIP_CART = os.environ.get("PC_GEN_SKIP_CART", "0") != "0"
+
+
 def make_class(cls, cart_d=False):
     g = ClassGen(*cls, cart_d=cart_d)
     g.gen_vrr()
@@ -964,7 +969,7 @@ def main(outdir):
     gens = {}
     for cart in (False, True):
         for cls in all_classes():
-            if cart and 2 not in cls:
+            if cart and (2 not in cls or SKIP_CART):
                 continue                      # no d shell: the spherical kernel is the kernel
             g = make_class(cls, cart_d=cart)
             path = os.path.join(outdir, "eri_%s.cu" % g.name)

@@ -31,10 +31,11 @@ def init(backend=None):
 
 
 def slice_bounds(total, rank, nranks):
-    """This rank's contiguous slice [begin, end) of a bucket pair's `total` tasks -- the same
-    arithmetic pc_plan (csrc/pc_api.cu) applies to every bucket pair (cost inside a bucket pair
-    is uniform, so equal slices are an exactly balanced static schedule; the slices of all
-    bucket pairs of a class run in one fused launch)."""
+    """Equal contiguous slices [begin, end) of `total` items -- the schedule the gloo tests of the
+    N>1 path use for host-side work.  pc_plan (csrc/pc_api.cu) does NOT cut this way: it cuts
+    every bucket pair at SEGMENT boundaries into nranks slices of equal modelled cost
+    (primitive quartets x flop_prim + quartets x per-quartet cost); the slices of all bucket
+    pairs of a class run in one fused launch."""
     begin = total * rank // nranks
     end = total * (rank + 1) // nranks
     return begin, end

@@ -70,6 +70,7 @@ class DeviceBasis:
         self.npair = t.nshell * (t.nshell + 1) // 2
         self.counts = None
         self._acc = None
+        self.ints_type = 0
 
     def close(self):
         if getattr(self, "h", None):
@@ -92,6 +93,18 @@ class DeviceBasis:
         import torch
         return torch.cuda.ExternalStream(self.stream_ptr(), device=self.device)
 
+    def _order_after_torch(self, *args):
+        """The library works on its own (non-blocking) stream.  When a caller hands over CUDA
+        tensors, they were produced -- or their memory was recycled by torch's caching allocator
+        -- on torch's current stream: make the library's stream wait for everything queued there
+        so far before it reads or overwrites them."""
+        if not any(hasattr(x, "is_cuda") and x.is_cuda for x in args):
+            return
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.torch_stream().wait_event(ev)
+
     def launch_count(self):
         n = ctypes.c_longlong()
         _lib.check(self.lib.pc_launch_count(self.h, ctypes.byref(n)))
@@ -103,7 +116,19 @@ class DeviceBasis:
         grid_value arguments of integrals.two_electron, Methods/integrals.py:427).  Switching
         drops the Schwarz factors and the plan."""
         _lib.check(self.lib.pc_basis_set_ints_type(self.h, int(ints_type), float(grid_value)))
+        key = (int(ints_type), float(grid_value) if int(ints_type) == 1 else None)
+        if key != getattr(self, "_ints_key", (0, None)):
+            # the C side dropped bounds, pair order and plan: forget ours, keep the slicing so
+            # that the next direct J/K re-plans for the same rank / nranks
+            if self.counts is not None:
+                self._replan = (self.counts["thresh"], self.counts["rank"], self.counts["nranks"])
+            self.counts = None
+        self._ints_key = key
         self.ints_type = int(ints_type)
+
+    def _ensure_plan(self):
+        if self.counts is None:
+            self.plan(*getattr(self, "_replan", (INTEGRAL_THRESHOLD, 0, 1)))
 
     def schwarz(self):
         """(bounds[npair,49], pmax[npair]); hartree_fock.py:244-254."""
@@ -177,6 +202,7 @@ class DeviceBasis:
         N = self.nbf
         G_dev = torch.empty((N, N, N, N), dtype=torch.float64, device="cuda:%d" % self.device)
         G_host = np.empty((N, N, N, N)) if to_host else None
+        self._order_after_torch(G_dev)          # the block may be recycled from pending torch work
         _lib.check(self.lib.pc_eri_tensor(self.h, _ptr(G_dev), _ptr(G_host)))
         return G_dev, G_host
 
@@ -194,6 +220,7 @@ class DeviceBasis:
     def jk_stored(self, G_dev, Dt, Da, Db):
         Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
         J, Xa, Xb = self._outputs(Dt)
+        self._order_after_torch(G_dev, Dt, Da, Db, J, Xa, Xb)
         _lib.check(self.lib.pc_jk_stored(self.h, _ptr(G_dev), _ptr(Dt), _ptr(Da), _ptr(Db),
                                          _ptr(J), _ptr(Xa), _ptr(Xb)))
         return J, Xa, Xb
@@ -209,11 +236,14 @@ class DeviceBasis:
         """Integral-direct J/K.  With an initialised torch.distributed process group and a plan
         built with nranks>1, partial accumulators are summed with one NCCL all-reduce."""
         Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
-        if self.counts is None:
-            self.plan()
+        if self.ints_type != 0:
+            raise _lib.PychemB200Error("jk_direct: J/K digestion is defined for the repulsion integrals; "
+                                       "call set_ints_type(0) (evaluate_2e_ints(molecule)) first")
+        self._ensure_plan()
         if variant is None and self.counts["nranks"] == 1:
             variant = AUTO                          # classified on the device inside pc_jk_direct
         J, Xa, Xb = self._outputs(Dt)
+        self._order_after_torch(Dt, Da, Db, J, Xa, Xb)
         if self.counts["nranks"] == 1:
             _lib.check(self.lib.pc_jk_direct(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db),
                                              _ptr(J), _ptr(Xa), _ptr(Xb)))
@@ -259,6 +289,7 @@ class DeviceBasis:
         """J/K for D[s] = (Dt, Da, Db), s = 0..nset-1, from the stored tensor: out[s] = (J, Xa, Xb)."""
         D, nset = self._batch_in(D)
         out = self._batch_out(D, nset)
+        self._order_after_torch(G_dev, D, out)
         _lib.check(self.lib.pc_jk_stored_batch(self.h, _ptr(G_dev), nset, _ptr(D), _ptr(out)))
         return out
 
@@ -266,9 +297,11 @@ class DeviceBasis:
         """Integral-direct J/K for all sets in one pass over the ERIs (general variant).  With a
         multi-rank plan the partial accumulators of all sets are summed with one all-reduce."""
         D, nset = self._batch_in(D)
-        if self.counts is None:
-            self.plan()
+        if self.ints_type != 0:
+            raise _lib.PychemB200Error("jk_direct_batch: J/K digestion is defined for the repulsion integrals")
+        self._ensure_plan()
         out = self._batch_out(D, nset)
+        self._order_after_torch(D, out)
         if self.counts["nranks"] == 1:
             _lib.check(self.lib.pc_jk_direct_batch(self.h, nset, _ptr(D), _ptr(out)))
             return out

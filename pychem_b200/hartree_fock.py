@@ -64,7 +64,12 @@ def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
             raise MemoryError("scattering integrals are consumed as a dense tensor (properties.py:22); "
                               "N^4 exceeds PYCHEM_B200_STORED_LIMIT_GB")
         mode = "stored"
-    st = {"mode": mode, "db": db, "G_dev": None, "molecule": molecule}
+    import weakref
+    try:
+        mref = weakref.ref(molecule)
+    except TypeError:
+        mref = (lambda m: (lambda: m))(molecule)
+    st = {"mode": mode, "db": db, "G_dev": None, "molecule": mref}
     if mode == "stored":
         G_dev, G_host = db.eri_tensor(engine.INTEGRAL_THRESHOLD, to_host=True)
         st["G_dev"] = G_dev
@@ -99,14 +104,23 @@ def _evict_other_molecules(molecule, keep=2):
         if st is not None:
             st["G_dev"] = None
             from . import integrals
-            integrals.release(st["molecule"])
+            integrals.release_key(old)
+
+
+def _state_for(molecule):
+    """The device state of `molecule`, (re)built by evaluate_2e_ints when it is missing, belongs
+    to an earlier geometry / basis of the same object (integrals.device_basis hands out a new
+    DeviceBasis then) or was left on the scattering integrals by a property job."""
+    st = _STATE.get(id(molecule))
+    if (st is None or st["molecule"]() is not molecule or st["db"].h is None
+            or st["db"] is not device_basis(molecule) or st["db"].ints_type != 0):
+        evaluate_2e_ints(molecule)
+        st = _STATE[id(molecule)]
+    return st
 
 
 def make_coulomb_exchange_matrices(molecule, this):
-    st = _STATE.get(id(molecule))
-    if st is None or st["molecule"] is not molecule or st["db"].h is None:
-        evaluate_2e_ints(molecule)
-        st = _STATE[id(molecule)]
+    st = _state_for(molecule)
     db = st["db"]
     Dt = np.ascontiguousarray(this.Total.Density, dtype=np.float64)
     Da = np.ascontiguousarray(this.Alpha.Density, dtype=np.float64)
@@ -130,10 +144,7 @@ def make_coulomb_exchange_matrices_batch(molecule, states):
     states = list(states)
     if not states:
         return
-    st = _STATE.get(id(molecule))
-    if st is None or st["molecule"] is not molecule or st["db"].h is None:
-        evaluate_2e_ints(molecule)
-        st = _STATE[id(molecule)]
+    st = _state_for(molecule)
     db = st["db"]
     N = int(molecule.NOrbitals)
     D = np.empty((len(states), 3, N, N))

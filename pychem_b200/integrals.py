@@ -17,16 +17,36 @@ from .engine import DeviceBasis
 _BASIS_CACHE = {}
 
 
+def _stamp(molecule):
+    """What the device tables of a molecule depend on: basis label, shell / function counts, the
+    Cartesian-shell choice and every atom's label and coordinates -- so a molecule that is mutated
+    in place (Atom.update_coords, Util/structures.py:827; a basis swap, :49-55) gets fresh
+    shell-pair tables, Schwarz bounds, one-electron matrices and ERI tensor.  (Edited exponents
+    under an unchanged basis label are not detected; call release(molecule) after such edits.)"""
+    atoms = tuple((getattr(a, "Label", None), float(getattr(a, "NuclearCharge", 0.0)),
+                   tuple(float(x) for x in a.Coordinates), len(a.Basis)) for a in molecule.Atoms)
+    cart = getattr(molecule, "CartesianL", None)
+    return (getattr(molecule, "Basis", None), int(molecule.NCgtf), int(molecule.NOrbitals),
+            tuple(cart) if cart is not None else None, atoms)
+
+
 def device_basis(molecule):
-    """One DeviceBasis per molecule object (rebuilt when the basis set was swapped,
-    cf. structures.update_basis, Util/structures.py:49-55)."""
+    """One DeviceBasis per molecule object, rebuilt when its stamp changes.  The cache holds the
+    molecule weakly: dropping the molecule frees its device state at the next lookup."""
+    import weakref
     key = id(molecule)
-    stamp = (getattr(molecule, "Basis", None), int(molecule.NCgtf), int(molecule.NOrbitals))
+    stamp = _stamp(molecule)
     ent = _BASIS_CACHE.get(key)
-    if ent is None or ent[0] != stamp or ent[2] is not molecule:
+    if ent is None or ent[0] != stamp or ent[2]() is not molecule:
         if ent is not None:
             ent[1].close()
-        ent = (stamp, DeviceBasis(molecule), molecule)
+        for k in [k for k, e in _BASIS_CACHE.items() if e[2]() is None]:     # owners that are gone
+            _BASIS_CACHE.pop(k)[1].close()
+        try:
+            ref = weakref.ref(molecule)
+        except TypeError:                       # an object without weak-reference support
+            ref = (lambda m: (lambda: m))(molecule)
+        ent = (stamp, DeviceBasis(molecule), ref)
         _BASIS_CACHE[key] = ent
     return ent[1]
 
@@ -38,6 +58,12 @@ def release(molecule=None):
         ent = _BASIS_CACHE.pop(k, None)
         if ent is not None:
             ent[1].close()
+
+
+def release_key(key):
+    ent = _BASIS_CACHE.pop(key, None)
+    if ent is not None:
+        ent[1].close()
 
 
 def shell_index_of(molecule, shell):

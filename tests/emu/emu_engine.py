@@ -85,8 +85,15 @@ class EmuBasis:
         except Exception:
             pass
 
+    ints_type = 0
+
     def set_ints_type(self, ints_type=0, grid_value=-1.0):
         self.check(self.lib.pc_basis_set_ints_type(self.h, int(ints_type), float(grid_value)))
+        key = (int(ints_type), float(grid_value) if int(ints_type) == 1 else None)
+        if key != getattr(self, "_ints_key", (0, None)):
+            self.counts = None            # the C side dropped its plan (as engine.DeviceBasis does)
+        self._ints_key = key
+        self.ints_type = int(ints_type)
 
     def schwarz(self):
         bounds = np.zeros((self.npair, 49))

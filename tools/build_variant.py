@@ -27,6 +27,9 @@ def main():
         emu = True
         args = args[1:]
     name, env = args[0], dict(a.split("=", 1) for a in args[1:])
+    nvcc_extra = env.pop("NVCC", "").split()          # e.g. NVCC="-DPC_ABL_NO_RED -DPC_BOYS_LDG256=1"
+    if not emu:
+        env.setdefault("PC_GEN_SKIP_CART", "1")       # timing variants: spherical kernels only
     os.environ.update(env)
     work = os.path.join("/tmp", "pychem_b200_variant_%s%s" % (name, "_emu" if emu else ""))
     csrc = os.path.join(work, "pychem_b200", "csrc")
@@ -60,14 +63,26 @@ def main():
     objdir = os.path.join(work, "obj")
     os.makedirs(objdir, exist_ok=True)
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-             "-diag-suppress", "177", "-diag-suppress", "550"]
+             "-diag-suppress", "177", "-diag-suppress", "550"] + nvcc_extra
     srcs = [os.path.join(csrc, "pc_api.cu"), os.path.join(csrc, "pc_mp2.cu"), os.path.join(csrc, "pc_generic.cu")] + sorted(
         os.path.join(csrc, "gen", f) for f in os.listdir(os.path.join(csrc, "gen")) if f.endswith(".cu"))
     srcs.sort(key=lambda p: -os.path.getsize(p))
 
+    import hashlib
+    hdr = hashlib.sha1(" ".join(flags).encode())
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cuh", ".h")):
+            hdr.update(open(os.path.join(csrc, f), "rb").read())
+    cache = os.path.join("/tmp", "pychem_b200_variant_objcache")
+    os.makedirs(cache, exist_ok=True)
+
     def cc(src):
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        subprocess.check_call(["nvcc"] + flags + ["-c", src, "-o", obj])
+        # objects are shared between variants when source, headers and flags agree
+        key = hashlib.sha1(hdr.hexdigest().encode() + open(src, "rb").read()).hexdigest()
+        obj = os.path.join(cache, os.path.basename(src)[:-3] + "." + key + ".o")
+        if not os.path.exists(obj):
+            subprocess.check_call(["nvcc"] + flags + ["-c", src, "-o", obj + ".tmp"])
+            os.replace(obj + ".tmp", obj)
         return obj
     with ThreadPoolExecutor(min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(cc, srcs))
