@@ -41,13 +41,16 @@ THRESH = 1.0e-8
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--waters", type=int, default=int(os.environ.get("PYCHEM_BENCH_WATERS", "32")))
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-classes", action="store_true", help="print per-class device times to stderr")
+    ap.add_argument("--sweep", default=os.environ.get("PYCHEM_BENCH_SWEEP", "8,16,32"),
+                    help="(H2O)n sizes of the BASELINE metric's sweep reported in the `sweep` array")
+    ap.add_argument("--no-stored", action="store_true", help="skip the stored-tensor leg ((H2O)8, 10.9 GB)")
     return ap.parse_args()
 
 
@@ -267,17 +270,55 @@ def algorithmic_flops(db, variant):
         mine += f_tot * share
         total += f_tot
         total_ref += (kb * kk * m["flop_prim"] + per_q) * tot
-        e = per_class.setdefault(name, {"flops": 0.0, "ms": 0.0, "quartets": 0})
+        e = per_class.setdefault(name, {"flops": 0.0, "ms": 0.0, "quartets": 0, "items": 0})
         e["flops"] += f_tot * share
         e["ms"] += float(t)
         e["quartets"] += int(cnt)
+        e["items"] += 1
     return mine, total, per_class, total_ref
+
+
+def committed_traffic(kernel_class):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel's launch from the
+    committed `ncu --set full` capture (profiles/ncu_traffic.json, written from the .ncu-rep by
+    tools/ncu_raw_summary.py); None when the capture holds no launch of that class."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            tab = json.load(fh)
+        e = tab.get("eri_%s_kernel<JK_RHF>" % kernel_class)
+        return (e["dram_bytes"], e["source"]) if e else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def sample_targets(n):
+    """Outputs compared with the oracle (same choice as tests/helpers.water_cluster_samples)."""
+    w = lambda k, s: 12 * (k % n) + s          # noqa: E731
+    j_pairs = [(w(0, 0), w(0, 0)), (w(0, 5), w(0, 5)), (w(0, 2), w(1, 4)), (w(0, 5), w(1, 7)),
+               (w(0, 3), w(5, 5)), (w(3, 8), w(3, 11)), (w(0, 4), w(n - 1, 4)), (w(7, 1), w(9, 5))]
+    return [(min(a, b), max(a, b)) for a, b in j_pairs], [w(0, 5), w(0, 4), w(n // 2, 0), w(n - 1, 8)]
+
+
+def oracle_check(table, n, Dt, Da, J, Xa):
+    """Part of the cpu_baseline leg (rank 0, N = 1): eight J blocks and four X rows of the bench
+    workload from the CPU oracle (oracle/eri_oracle.c, orc_jk_sample) against the device result."""
+    from oracle import oracle
+    t0 = time.perf_counter()
+    ob = oracle.OracleBasis(table)
+    _, pm = ob.schwarz()
+    jp, ks = sample_targets(n)
+    J0, Xa0, _, mJ, mX, nq = oracle.jk_sample(ob, Dt, Da, Da, jp, ks, thresh=THRESH, pmax=pm)
+    return {"max_abs_diff_J": float(np.abs(J - J0)[mJ].max()), "max_abs_diff_Xa": float(np.abs(Xa - Xa0)[mX].max()),
+            "entries_J": int(mJ.sum()), "entries_Xa": int(mX.sum()), "oracle_quartets": int(nq),
+            "seconds": time.perf_counter() - t0,
+            "what": "8 Coulomb blocks + 4 exchange rows of this workload from oracle/eri_oracle.c (orc_jk_sample: "
+                    "reference screening hartree_fock.py:276-295, contraction :345-347) vs the device-timed result"}
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from pychem_b200 import dist as pdist, engine, hartree_fock as hf_gpu, structures as S
+    from pychem_b200 import _lib, dist as pdist, engine, hartree_fock as hf_gpu, integrals as ints_gpu, structures as S
 
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout for the ONE JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -286,176 +327,208 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-
-    n = args.waters
-    mol = S.Molecule(S.water_cluster(n), "6-31G**")
-    N = mol.NOrbitals
-    t_setup = time.perf_counter()
-    db = engine.DeviceBasis(mol, device=local)
-    t_basis = time.perf_counter() - t_setup
-    db.schwarz()
-    t_schwarz = time.perf_counter() - t_setup - t_basis
-    counts = db.plan(THRESH, rank, world)
-    t_plan = time.perf_counter() - t_setup - t_basis - t_schwarz
-    variant = engine.RHF
-
-    # synthetic symmetric density: D = (X + X^T)/2, X ~ U(-1,1), seed 1234
-    rng = np.random.default_rng(1234)
-    X = rng.uniform(-1, 1, (N, N))
-    Da_h = 0.5 * (X + X.T)
-    Dt_h = 2.0 * Da_h
-    Dt_d = torch.from_numpy(Dt_h).to(dev)
-    Da_d = torch.from_numpy(Da_h).to(dev)
-    J_d = torch.empty((N, N), dtype=torch.float64, device=dev)
-    Xa_d = torch.empty_like(J_d)
-    Xb_d = torch.empty_like(J_d)
-    acc = db.accumulator()
-    stream = db.torch_stream()
-    lib = db.lib
-    from pychem_b200 import _lib
+    os.environ["PYCHEM_B200_MODE"] = "direct"
     P = engine._ptr
-
-    def step_device():
-        _lib.check(lib.pc_jk_direct_accumulate(db.h, variant, P(Dt_d), P(Da_d), P(Da_d), P(acc)))
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_reduce(acc, op=dist.ReduceOp.SUM)
-        _lib.check(lib.pc_jk_finalize(db.h, variant, P(acc), P(J_d), P(Xa_d), P(Xb_d)))
+    variant = engine.RHF
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        for _ in range(steps):
-            fn()
-        e1.record(stream)
-        e1.synchronize()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+    class Case:
+        """One (H2O)n molecule set up through the plugin (evaluate_2e_ints) + device-resident buffers."""
 
-    # clocks are sampled (nvidia-smi, 100 ms period) from the warm-up through the timed region:
-    # a Fock build is ~20 ms, so short runs would otherwise see no sample at all
+        def __init__(self, n):
+            self.n = n
+            self.mol = S.Molecule(S.water_cluster(n), "6-31G**")
+            self.N = self.mol.NOrbitals
+            t0 = time.perf_counter()
+            self.db = ints_gpu.device_basis(self.mol)
+            self.t_basis = time.perf_counter() - t0
+            self.db.schwarz()
+            self.t_schwarz = time.perf_counter() - t0 - self.t_basis
+            hf_gpu.evaluate_2e_ints(self.mol)                   # Bounds + plan for this rank's slice
+            self.t_plan = time.perf_counter() - t0 - self.t_basis - self.t_schwarz
+            self.counts = self.db.counts
+            assert self.counts["rank"] == rank and self.counts["nranks"] == world
+            # synthetic symmetric density (SURVEY 8(d)): D = (X + X^T)/2, X ~ U(-1,1), seed 1234
+            X = np.random.default_rng(1234).uniform(-1, 1, (self.N, self.N))
+            self.Da_h = 0.5 * (X + X.T)
+            self.Dt_h = 2.0 * self.Da_h
+            self.Dt_d = torch.from_numpy(self.Dt_h).to(dev)
+            self.Da_d = torch.from_numpy(self.Da_h).to(dev)
+            self.J_d = torch.empty((self.N, self.N), dtype=torch.float64, device=dev)
+            self.Xa_d = torch.empty_like(self.J_d)
+            self.Xb_d = torch.empty_like(self.J_d)
+            self.acc = self.db.accumulator()
+            self.stream = self.db.torch_stream()
+            torch.cuda.synchronize()
+
+        def step_device(self, v=None):
+            db, lib = self.db, self.db.lib
+            _lib.check(lib.pc_jk_direct_accumulate(db.h, variant if v is None else v, P(self.Dt_d), P(self.Da_d),
+                                                   P(self.Da_d), P(self.acc)))
+            if v is not None:
+                return
+            if world > 1:
+                with torch.cuda.stream(self.stream):
+                    dist.all_reduce(self.acc, op=dist.ReduceOp.SUM)
+            _lib.check(lib.pc_jk_finalize(db.h, variant, P(self.acc), P(self.J_d), P(self.Xa_d), P(self.Xb_d)))
+
+        def timed(self, fn, steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for _ in range(steps):
+                fn()
+            e1.record(self.stream)
+            e1.synchronize()
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item())
+
+    main = Case(args.waters)
+    n, N, db, counts = main.n, main.N, main.db, main.counts
+    lib = db.lib
+
+    # clocks are sampled (nvidia-smi, 100 ms period) from the warm-up through the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        step_device()
+        main.step_device()
     launches0 = db.launch_count()
-    ms_total = timed(step_device, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_total = main.timed(main.step_device, args.steps)
     launches = (db.launch_count() - launches0) // max(args.steps, 1)
     ms_step = ms_total / args.steps
     value = counts["all_eris"] / (ms_step * 1e-3)
+    # a timed region of >= 2 s beside the K steps the caller asked for (same steps, same timing)
+    sustained = None
+    if ms_total < 2000.0:
+        n_more = int(2000.0 / max(ms_step, 1e-3)) + 1
+        ms_more = main.timed(main.step_device, n_more)
+        sustained = {"steps": n_more, "ms_per_step": ms_more / n_more, "seconds": ms_more * 1e-3,
+                     "value": counts["all_eris"] / (ms_more / n_more * 1e-3)}
+    clocks = sampler.stop() if rank == 0 else None
+    J_dev_host = main.J_d.cpu().numpy()
+    Xa_dev_host = main.Xa_d.cpu().numpy()
 
-    if ms_total < 400.0:
-        # timed region shorter than a few nvidia-smi periods: keep the same load running for
-        # ~0.5 s (same iteration count on every rank) and sample the clocks under it
-        n_extra = int(500.0 / max(ms_step, 1e-3)) + 1
-        sampler2 = ClockSampler(local)
-        if rank == 0:
-            sampler2.start()
-        for _ in range(n_extra):
-            step_device()
-        barrier()
-        if rank == 0:
-            extra = sampler2.stop()
-            if extra.get("samples", 0) > clocks.get("samples", 0):
-                clocks = extra
-                clocks["note"] = ("timed region of %.0f ms is shorter than a few nvidia-smi periods; sampled over "
-                                  "%d more identical steps right after it" % (ms_total, n_extra))
     # ---- e2e through the plugin call with host buffers --------------------------------------
-    hf_gpu._STATE[id(mol)] = {"mode": "direct", "db": db, "G_dev": None, "molecule": mol}
-    Dt_p = torch.from_numpy(Dt_h).pin_memory()
-    Da_p = torch.from_numpy(Da_h).pin_memory()
-    state = _State(Dt_p.numpy(), Da_p.numpy(), Da_p.numpy())
+    def e2e_run(pinned):
+        if pinned:
+            Dt_p, Da_p = torch.from_numpy(main.Dt_h).pin_memory(), torch.from_numpy(main.Da_h).pin_memory()
+            state = _State(Dt_p.numpy(), Da_p.numpy(), Da_p.numpy().copy())
+            state._keep = (Dt_p, Da_p)
+        else:
+            # what the reference's SCF driver hands over: three distinct pageable numpy arrays
+            state = _State(main.Dt_h.copy(), main.Da_h.copy(), main.Da_h.copy())
+        for _ in range(max(args.warmup, 3)):
+            hf_gpu.make_coulomb_exchange_matrices(main.mol, state)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            hf_gpu.make_coulomb_exchange_matrices(main.mol, state)
+        barrier()
+        t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), state
 
-    def step_e2e():
-        hf_gpu.make_coulomb_exchange_matrices(mol, state)
-
-    for _ in range(max(args.warmup, 3)):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms.item())
+    e2e_ms, state = e2e_run(pinned=True)
+    e2e_page_ms, _ = e2e_run(pinned=False)
     e2e_value = counts["all_eris"] / (e2e_ms * 1e-3)
-    err = float(np.abs(state.Total.Coulomb - J_d.cpu().numpy()).max())
+    err = float(np.abs(state.Total.Coulomb - J_dev_host).max())
 
     # ---- roofline: per-class device times (one profiled build), FP64 peak measured live ------
     db.set_profiling(True)
-    _lib.check(lib.pc_jk_direct_accumulate(db.h, variant, P(Dt_d), P(Da_d), P(Da_d), P(acc)))
+    main.step_device(v=variant)
     db.set_profiling(False)
     my_flops, all_flops, per_class, ref_flops = algorithmic_flops(db, variant)
     peak = engine.fp64_peak_tflops(local)
     top = max(per_class.items(), key=lambda kv: kv[1]["ms"])
     eri_ms = sum(v["ms"] for v in per_class.values())
     achieved = all_flops / (ms_step * 1e-3) / 1e12 / world      # per-GPU TFLOP/s over the whole step
-    # dominant kernel = the class kernel with the largest share of the step (per-launch CUDA-event
-    # times of one profiled build).  `traffic`: DRAM bytes of its (fused) launch from the committed
-    # ncu --set full capture (profiles/r1b_final_ncu_full_psss.txt) -- everything is
-    # L2-resident, the path is not HBM-bound.
     top_tf = top[1]["flops"] / (top[1]["ms"] * 1e-3) / 1e12 if top[1]["ms"] else None
-    roofline = {"bound": "fp64", "achieved": top_tf, "peak": peak, "unit": "TFLOP/s",
-                "frac": (top_tf / peak) if (top_tf and peak) else None,
-                "traffic": 44.9e6 if top[0] == "psss" else None,
-                "kernel": "eri_%s_kernel<JK_RHF>: one fused launch per build covering its %d bucket pairs, %.3f ms "
-                          "alone, %.1f%% of the serialised per-class total"
-                          % (top[0], sum(1 for c in db.plan_items()[0] if "spd"[c[0]] + "spd"[c[1]] + "spd"[c[2]] + "spd"[c[3]] == top[0]),
-                             top[1]["ms"], 100.0 * top[1]["ms"] / eri_ms if eri_ms else 0.0),
+    traffic, traffic_src = committed_traffic(top[0])
+    # `frac` = the WHOLE STEP (all class kernels + finalize of one Fock build): no single kernel
+    # holds more than ~1/6 of the step, so the whole-step fraction is the honest headline; the
+    # dominant kernel is reported beside it
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "kernels": "all %d launches of one Fock build (eri_*_kernel<JK_RHF> per class + finalize), concurrent on "
+                           "8 streams, replayed as one CUDA graph" % launches,
+                "algorithmic_gflop_per_step": all_flops / 1e9,
+                "reference_unscreened_gflop_per_step": ref_flops / 1e9,
+                "serialised_kernel_ms_over_step_ms": eri_ms / ms_step if ms_step else None,
+                "dominant_kernel": {"name": "eri_%s_kernel<JK_RHF>" % top[0], "ms": top[1]["ms"],
+                                    "share_of_serialised_step": top[1]["ms"] / eri_ms if eri_ms else None,
+                                    "achieved": top_tf, "frac": (top_tf / peak) if (top_tf and peak) else None,
+                                    "bucket_pairs_in_launch": top[1]["items"], "traffic": traffic,
+                                    "traffic_source": traffic_src},
                 "peak_source": "pc_fp64_peak: register-resident DFMA loop measured in this run "
                                "(MEASURED_PEAKS.json has no FP64 entry)",
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the fused eri_psss launch, ncu --set "
-                                  "full, profiles/r1b_final_ncu_full_psss.txt (35.6 MB read + 9.3 MB written; pair tables, Boys table, densities "
-                                  "and accumulators are L2-resident: the kernel is LSU/atomic-bound, not HBM-bound)",
-                "whole_step": {"achieved": achieved, "frac": achieved / peak if peak else None,
-                               "kernels": "all %d launches of one Fock build (21 eri_*_kernel<JK_RHF> + finalize), concurrent "
-                                          "on 8 streams, replayed as one CUDA graph" % launches,
-                               "algorithmic_gflop_per_step": all_flops / 1e9,
-                               "reference_unscreened_gflop_per_step": ref_flops / 1e9,
-                               "serialised_kernel_ms_over_step_ms": eri_ms / ms_step if ms_step else None},
-                "fp64_instruction_bound": {
-                    "dominant_kernel_frac_ceiling": 0.407 if top[0] == "psss" else None,
-                    "whole_step_frac_ceiling": 0.707,
-                    "note": "static SASS count of the built kernels (tools/sass_mix.py, profiles/r1d_sass_instruction_mix.txt): "
-                            "FP64-pipe instructions actually executed per primitive quartet vs the flop model above -- the "
-                            "share of the FP64 peak a perfectly pipelined loop of the present code could show under that model"},
                 "flop_count": "executed primitive quartets (after the 1e-24 primitive-pair cut-off) * flop_prim "
                               "+ quartets * (flop_cont + digestion), SURVEY 8(d) model on the generator's DAG "
                               "(pychem_b200/data/flop_model.json)"}
+
     # pure ERI generation (same schedule, integrals discarded): the "FP64 ERIs/sec" of generation
-    def step_eri_only():
-        _lib.check(lib.pc_jk_direct_accumulate(db.h, 5, P(Dt_d), P(Da_d), P(Da_d), P(acc)))
-    step_eri_only()
-    eri_only_ms = timed(step_eri_only, max(args.steps, 2)) / max(args.steps, 2)
+    main.step_device(v=5)
+    eri_only_ms = main.timed(lambda: main.step_device(v=5), max(args.steps, 2)) / max(args.steps, 2)
     if args.profile_classes and rank == 0:
         db.set_profiling(True)
-        step_eri_only()
+        main.step_device(v=5)
         db.set_profiling(False)
         cls2, _, _, ms2 = db.plan_items()
         gen = {}
         for (l1, l2, l3, l4), t in zip(cls2, ms2):
             nm = "spd"[l1] + "spd"[l2] + "spd"[l3] + "spd"[l4]
             gen[nm] = gen.get(nm, 0.0) + float(t)
-        for k, v in per_class.items():
-            v["gen_ms"] = gen.get(k, 0.0)
-    if args.profile_classes and rank == 0:
         for k, v in sorted(per_class.items(), key=lambda kv: -kv[1]["ms"]):
             tf = v["flops"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] else 0.0
             print("class %s: %9.3f ms (generation only %7.3f ms)  %12d quartets  %7.3f TFLOP/s (%.1f%% of peak)"
-                  % (k, v["ms"], v.get("gen_ms", 0.0), v["quartets"], tf, 100 * tf / peak), file=sys.stderr)
+                  % (k, v["ms"], gen.get(k, 0.0), v["quartets"], tf, 100 * tf / peak), file=sys.stderr)
+
+    # ---- checks: checksums of the result (comparable across N) ---------------------------------
+    main.step_device()
+    barrier()
+    J_h, Xa_h = main.J_d.cpu().numpy(), main.Xa_d.cpu().numpy()
+    checks = {"J_fro": float(np.linalg.norm(J_h)), "Xa_fro": float(np.linalg.norm(Xa_h)), "J_00": float(J_h[0, 0]),
+              "Xa_00": float(Xa_h[0, 0]), "J_trace": float(np.trace(J_h)),
+              "e2e_max_abs_diff_vs_device_path": err}
+
+    # ---- the BASELINE metric's sweep: (H2O)n, n = 8..32 ------------------------------------------
+    sweep = []
+    for nw in [int(x) for x in args.sweep.split(",") if x]:
+        if nw == n:
+            sweep.append({"waters": n, "basis_functions": N, "fock_build_ms": ms_step, "value": value, "unit": UNIT,
+                          "quartets": counts["all_quartets"], "eris": counts["all_eris"],
+                          "roofline_frac": roofline["frac"]})
+            continue
+        c = Case(nw)
+        for _ in range(3):
+            c.step_device()
+        k_steps = max(args.steps, 10)
+        t = c.timed(c.step_device, k_steps) / k_steps
+        _, fl, _, _ = algorithmic_flops(c.db, variant)
+        sweep.append({"waters": nw, "basis_functions": c.N, "fock_build_ms": t,
+                      "value": c.counts["all_eris"] / (t * 1e-3), "unit": UNIT,
+                      "quartets": c.counts["all_quartets"], "eris": c.counts["all_eris"],
+                      "roofline_frac": fl / (t * 1e-3) / 1e12 / world / peak if peak else None})
+        hf_gpu.release(c.mol)
+        ints_gpu.release(c.mol)
+        del c
+    sweep.sort(key=lambda e: e["waters"])
+
+    # ---- stored-tensor mode at (H2O)8 (N = 192, 10.9 GB): HBM roofline of the streaming J/K ----
+    stored = None
+    if rank == 0 and world == 1 and not args.no_stored:
+        try:
+            stored = stored_mode_leg(torch, engine, S, dev, args)
+        except Exception as exc:
+            stored = {"error": repr(exc)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -463,6 +536,10 @@ def run_b200(args):
             cpu = reference_sample(n, args.cpu_seconds)
         except Exception as exc:      # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "unavailable", "sample": repr(exc)}
+        try:
+            checks["oracle"] = oracle_check(db.table, n, main.Dt_h, main.Da_h, J_h, Xa_h)
+        except Exception as exc:
+            checks["oracle"] = {"error": repr(exc)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -477,20 +554,73 @@ def run_b200(args):
                                         "by >1e8 quartets per step; no reuse between steps is possible "
                                         "(each step overwrites the accumulators)"},
                 "fock_build_ms": ms_step,
-                "setup_seconds": {"basis_tables": t_basis, "schwarz": t_schwarz, "plan": t_plan,
+                "sustained": sustained,
+                "setup_seconds": {"basis_tables": main.t_basis, "schwarz": main.t_schwarz, "plan": main.t_plan,
                                   "note": "once per geometry, outside the timed region"},
                 "eri_generation_only": {"ms_per_pass": eri_only_ms, "value": counts["all_eris"] / (eri_only_ms * 1e-3), "unit": UNIT},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": 3 * N * N * 8, "d2h_bytes_per_step": 3 * N * N * 8,
-                        "max_abs_diff_vs_device_path": err},
+                        "call": "pychem_b200.hartree_fock.make_coulomb_exchange_matrices(molecule, state), pinned host "
+                                "densities in, J / X host arrays out",
+                        "pageable_inputs": {"ms_per_step": e2e_page_ms, "value": counts["all_eris"] / (e2e_page_ms * 1e-3),
+                                            "note": "three distinct pageable numpy arrays, as the reference's SCF driver passes"}},
                 "gpu_launches": int(launches),
                 "roofline": roofline,
+                "checks": checks,
+                "sweep": sweep,
+                "stored_mode": stored,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    db.close()
+    hf_gpu.release()
+    ints_gpu.release()
     if world > 1:
         dist.destroy_process_group()
+
+
+def stored_mode_leg(torch, engine, S, dev, args):
+    """(H2O)8 6-31G**: dense tensor build (8-fold scatter) and the streaming J/K pass over it."""
+    mol = S.Molecule(S.water_cluster(8), "6-31G**")
+    db = engine.DeviceBasis(mol, device=dev.index)
+    N = db.nbf
+    db.schwarz()
+    stream = db.torch_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    G_dev, _ = db.eri_tensor(THRESH, to_host=False)            # warm-up (plan + first touch)
+    e0.record(stream)
+    from pychem_b200 import _lib
+    _lib.check(db.lib.pc_eri_tensor(db.h, engine._ptr(G_dev), None))
+    e1.record(stream)
+    e1.synchronize()
+    tensor_ms = e0.elapsed_time(e1)
+    X = np.random.default_rng(1234).uniform(-1, 1, (N, N))
+    Da = torch.from_numpy(0.5 * (X + X.T)).to(dev)
+    Dt = 2.0 * Da
+    torch.cuda.synchronize()
+    for _ in range(3):
+        db.jk_stored(G_dev, Dt, Da, Da)
+    reps = 20
+    e0.record(stream)
+    for _ in range(reps):
+        db.jk_stored(G_dev, Dt, Da, Da)
+    e1.record(stream)
+    e1.synchronize()
+    jk_ms = e0.elapsed_time(e1) / reps
+    try:
+        peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        src = "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, ValueError, KeyError):
+        peak, src = 6550.0, "fallback (tools guide): 6.55 TB/s"
+    gbs = 8.0 * N ** 4 / (jk_ms * 1e-3) / 1e9
+    out = {"workload": "(H2O)8 6-31G** stored-tensor mode, N=%d, tensor %.1f GB" % (N, 8.0 * N ** 4 / 1e9),
+           "tensor_build_ms": tensor_ms, "jk_ms": jk_ms,
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "algorithmic_bytes": 8.0 * N ** 4, "peak_source": src,
+                        "note": "one streaming pass over the tensor per Fock build (the reference's three einsum passes read 24 N^4 bytes); "
+                                "tensor larger than L2, timed over %d consecutive passes" % reps}}
+    del G_dev
+    db.close()
+    return out
 
 
 def main():

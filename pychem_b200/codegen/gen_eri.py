@@ -424,8 +424,7 @@ class ClassGen:
         s.append("  const int block = %d;" % block)
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
-        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
-                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT", "PC_MODE_JK_GEN_BATCH"):
+        for mode in MODES:
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")
@@ -589,8 +588,7 @@ class ClassGen:
         s.append("  const int block = %d;" % block)
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
-        for mode in ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
-                     "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT", "PC_MODE_JK_GEN_BATCH"):
+        for mode in MODES:
             s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")
@@ -920,6 +918,14 @@ if os.environ.get("PC_GEN_RUN_CLASSES") is not None:
     RUN_CLASSES = dict((kv.split("=")[0], int(kv.split("=")[1]))
                        for kv in os.environ["PC_GEN_RUN_CLASSES"].split(",") if kv)
 
+
+# output modes instantiated per class kernel; timing variants (tools/build_variant.py) restrict them
+# with PC_GEN_MODES=0,2,5 (BLOCKS for the Schwarz pass, JK_RHF, NULL): a third of the compile time
+ALL_MODES = ("PC_MODE_BLOCKS", "PC_MODE_TENSOR", "PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL",
+             "PC_MODE_BLOCKS_SCAT", "PC_MODE_TENSOR_SCAT", "PC_MODE_JK_GEN_BATCH")
+MODES = ALL_MODES
+if os.environ.get("PC_GEN_MODES"):
+    MODES = tuple(ALL_MODES[int(k)] for k in os.environ["PC_GEN_MODES"].split(","))
 
 # A/B variant builds (tools/build_variant.py) skip the Cartesian-d kernels: the dispatch table then
 # points at the spherical ones, which is wrong for Cartesian_L = [2] molecules and fine for timing

@@ -30,6 +30,7 @@ def main():
     nvcc_extra = env.pop("NVCC", "").split()          # e.g. NVCC="-DPC_ABL_NO_RED -DPC_BOYS_LDG256=1"
     if not emu:
         env.setdefault("PC_GEN_SKIP_CART", "1")       # timing variants: spherical kernels only
+        env.setdefault("PC_GEN_MODES", "0,2,5")       # ... in the modes the A/B harness runs
     os.environ.update(env)
     work = os.path.join("/tmp", "pychem_b200_variant_%s%s" % (name, "_emu" if emu else ""))
     csrc = os.path.join(work, "pychem_b200", "csrc")

@@ -25,4 +25,13 @@ for cls in psss ppps dpps; do
   python tools/ncu_source_dump.py /tmp/${cls}2.ncu-rep "eri_${cls}_kernel" >> $O/ncu_${cls}2.log 2>&1
   mv gpurun_out/src_eri_${cls}_kernel.csv.gz $O/src_${cls}_mode2.csv.gz 2>/dev/null
 done
+timeout 600 python bench.py --steps 10 --warmup 3 --cpu-seconds 5 --profile-classes > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -3 $O/bench.err
+python - <<'PY'
+import json
+try:
+    d=json.load(open('gpurun_out/r2c1/bench.json'))
+    print('ms', d['ms_per_step'], 'e2e', d['e2e']['ms_per_step'], d['e2e']['pageable_inputs']['ms_per_step'], 'frac', d['roofline']['frac'])
+    print('checks', d['checks']); print('sweep', d['sweep']); print('stored', d['stored_mode'])
+except Exception as e: print('bench parse failed', e)
+PY
 ls -la $O
