@@ -1171,8 +1171,29 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
   {
     constexpr int NBG = 4;                       // slabs per CTA
     const int ngrp = (N + NBG - 1) / NBG;
-    if (N % 2 == 0) jk_stored_kernel<2, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
-    else jk_stored_kernel<1, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+    static const bool no_tma = getenv("PYCHEM_B200_STORED_NO_TMA") != nullptr;      // A/B switch
+    if (N % 2 == 0 && N >= 8 && !no_tma) {
+      // TMA-staged kernel: ~24 KB tiles (rt rows of the NBG slabs), 4 in flight per CTA
+      constexpr int STAGES = 4;
+      const int rt = std::max(1, (int)(24576 / ((size_t)NBG * N * sizeof(double))));
+      const int ct = std::min(256, ((N / 2 + 31) / 32) * 32);      // threads along the columns (pairs)
+      const int rgn = std::max(1, 256 / ct);
+      const size_t smem = ((size_t)STAGES * NBG * rt * N + (size_t)2 * NBG * N + (size_t)2 * rgn * 2 * ct) * sizeof(double);
+      if (N / 2 <= 256 && smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          PC_CUDA(cudaFuncSetAttribute(jk_stored_tma_kernel<NBG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+          attr_set = true;
+        }
+        jk_stored_tma_kernel<NBG, STAGES><<<N * ngrp, 256, smem, h->stream>>>(N, ngrp, rt, ct, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+      } else {
+        jk_stored_kernel<2, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+      }
+    } else if (N % 2 == 0) {
+      jk_stored_kernel<2, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+    } else {
+      jk_stored_kernel<1, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+    }
   }
   PC_CUDA(cudaGetLastError());
   h->launches += 1;

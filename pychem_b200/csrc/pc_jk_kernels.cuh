@@ -4,6 +4,7 @@
 //   J/K from the stored tensor  Methods/hartree_fock.py:345-347 (three einsum passes in the reference)
 #pragma once
 #include "pc_common.cuh"
+#include "pc_async.cuh"
 
 namespace {
 
@@ -116,6 +117,127 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const d
     double sum = 0.0;
     for (int k = 0; k < RG; ++k) sum += red[0][k][threadIdx.x];
     J[(size_t)a * N + b0 + threadIdx.x] = sum;
+  }
+}
+
+// The same contraction with the tensor staged through shared memory by the TMA engine
+// (`cp.async.bulk`, pc_async.cuh): a CTA owns NB consecutive slabs G[a, b0..b0+NB-1, :, :]; one
+// tile = `rt` rows c of all NB slabs (NB contiguous pieces of rt*N doubles), STAGES tiles in
+// flight per CTA behind full / empty mbarriers.  Thread 0 issues the copies -- no registers and
+// no LSU slots are spent on the 8 N^4 bytes -- everybody consumes: a thread owns the column pair
+// (d, d+1) of one row group for the whole CTA, so X[a, d] stays in registers until the end and
+// the row groups meet once, in shared memory.  Needs N even (16-byte rows); odd N keeps
+// jk_stored_kernel.  Dynamic shared memory: stage buffers | Da/Db columns | reduction scratch.
+template <int NB, int STAGES>
+__global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int rt, int ct,
+                                                            const double* __restrict__ G,
+                                                            const double* __restrict__ Dt,
+                                                            const double* __restrict__ Da,
+                                                            const double* __restrict__ Db,
+                                                            double* __restrict__ J,
+                                                            double* __restrict__ Xa,
+                                                            double* __restrict__ Xb) {
+  PC_DYN_SMEM(smem_raw);
+  __shared__ PcMbar full[STAGES], empty[STAGES];
+  __shared__ double jred[8][NB];
+  const int a = blockIdx.x / ngrp, b0 = (blockIdx.x % ngrp) * NB;
+  const int nbv = min(NB, N - b0);
+  const size_t NN = (size_t)N * N;
+  const double* __restrict__ slab = G + ((size_t)a * N + b0) * NN;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const size_t tile_doubles = (size_t)NB * rt * N;                 // one stage
+  double* stage0 = reinterpret_cast<double*>(smem_raw);
+  double* sD = stage0 + (size_t)STAGES * tile_doubles;            // [2][NB][N]: Da[c, b0+k], Db[c, b0+k]
+  double* sX = sD + (size_t)2 * NB * N;                            // [2][rgn][2 ct]
+  const int ntiles = (N + rt - 1) / rt;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { pc_mbar_init(&full[s], 1); pc_mbar_init(&empty[s], nthr); }
+    pc_mbar_fence_init();
+  }
+  __syncthreads();
+  auto issue = [&](int t) {                                        // thread 0 only
+    const int s = t % STAGES;
+    const int rows = min(rt, N - t * rt);
+    const unsigned bytes = (unsigned)((size_t)rows * N * sizeof(double));
+    pc_mbar_arrive_expect_tx(&full[s], bytes * (unsigned)nbv);
+    for (int k = 0; k < nbv; ++k)
+      pc_bulk_g2s(stage0 + (size_t)s * tile_doubles + (size_t)k * rt * N, slab + (size_t)k * NN + (size_t)t * rt * N, bytes, &full[s]);
+  };
+  if (tid == 0)
+    for (int t = 0; t < min(STAGES, ntiles); ++t) issue(t);
+  // the density columns this CTA needs for the exchange part
+  for (int idx = tid; idx < N * NB; idx += nthr) {
+    const int c = idx / NB, k = idx % NB;
+    const bool ok = k < nbv;
+    sD[(size_t)k * N + c] = ok ? __ldg(Da + (size_t)c * N + b0 + k) : 0.0;
+    sD[(size_t)(NB + k) * N + c] = ok ? __ldg(Db + (size_t)c * N + b0 + k) : 0.0;
+  }
+  __syncthreads();
+  const int rgn = nthr / ct;                                       // row groups
+  const int cg = tid % ct, rgi = tid / ct;
+  const int d = 2 * cg;
+  const bool active = d < N && rgi < rgn;
+  double jsum[NB], xa0 = 0.0, xa1 = 0.0, xb0 = 0.0, xb1 = 0.0;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) jsum[k] = 0.0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % STAGES;
+    pc_mbar_wait(&full[s], (unsigned)((t / STAGES) & 1));
+    if (active) {
+      const int rows = min(rt, N - t * rt);
+      const double* __restrict__ st = stage0 + (size_t)s * tile_doubles;
+      for (int r = rgi; r < rows; r += rgn) {
+        const int c = t * rt + r;
+        const double2 t2 = __ldg(reinterpret_cast<const double2*>(Dt + (size_t)c * N + d));
+#pragma unroll
+        for (int k = 0; k < NB; ++k) {
+          // slabs beyond the tensor (k >= nbv) were never copied: their density factors are 0 and
+          // the stage words are whatever an earlier tile left -- skip them (uniform per CTA)
+          if (k < nbv) {
+            const double2 g2 = *reinterpret_cast<const double2*>(st + ((size_t)k * rt + r) * N + d);
+            const double da = sD[(size_t)k * N + c], db = sD[(size_t)(NB + k) * N + c];
+            jsum[k] = fma(t2.x, g2.x, jsum[k]);
+            jsum[k] = fma(t2.y, g2.y, jsum[k]);
+            xa0 = fma(da, g2.x, xa0); xa1 = fma(da, g2.y, xa1);
+            xb0 = fma(db, g2.x, xb0); xb1 = fma(db, g2.y, xb1);
+          }
+        }
+      }
+    }
+    pc_mbar_arrive(&empty[s]);
+    // refill the stage of the PREVIOUS tile: by now everybody has normally left it
+    if (tid == 0 && t >= 1 && t - 1 + STAGES < ntiles) {
+      const int sp = (t - 1) % STAGES;
+      pc_mbar_wait(&empty[sp], (unsigned)(((t - 1) / STAGES) & 1));
+      issue(t - 1 + STAGES);
+    }
+  }
+  // ---- exchange: sum the row groups, one atomic per column (the ngrp CTAs of row a meet here)
+  if (rgi < rgn) {
+    sX[((size_t)0 * rgn + rgi) * 2 * ct + 2 * cg] = xa0; sX[((size_t)0 * rgn + rgi) * 2 * ct + 2 * cg + 1] = xa1;
+    sX[((size_t)1 * rgn + rgi) * 2 * ct + 2 * cg] = xb0; sX[((size_t)1 * rgn + rgi) * 2 * ct + 2 * cg + 1] = xb1;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 2 * N; idx += nthr) {
+    const int which = idx / N, col = idx % N;
+    double sum = 0.0;
+    for (int g = 0; g < rgn; ++g) sum += sX[((size_t)which * rgn + g) * 2 * ct + col];
+    atomicAdd((which ? Xb : Xa) + (size_t)a * N + col, -sum);
+  }
+  // ---- Coulomb: block sum of the NB partial dot products
+  const int lane = tid & 31, w = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    double v = active ? jsum[k] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) jred[w][k] = v;
+  }
+  __syncthreads();
+  if (tid < nbv) {
+    double sum = 0.0;
+    for (int k = 0; k < (nthr >> 5); ++k) sum += jred[k][tid];
+    J[(size_t)a * N + b0 + tid] = sum;
   }
 }
 

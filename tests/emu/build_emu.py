@@ -73,6 +73,8 @@ def transform(text, name):
     def repl(m):
         kern, cfg, args = m.group(1), _split_args(m.group(2)), m.group(3)
         return "pcemu::launch((unsigned)(%s), (unsigned)(%s), [&] { %s(%s); });" % (cfg[0], cfg[1], kern, args)
+    # real-PTX regions that have a functional model under PC_HOST_EMU (pc_async.cuh)
+    text = re.sub(r"// PC_EMU_SKIP_BEGIN.*?// PC_EMU_SKIP_END", "", text, flags=re.S)
     text, n = LAUNCH.subn(repl, text)
     if name == "pc_common.cuh":
         if RSQRT_ASM not in text or PREFETCH_ASM not in text or LDG256_ASM not in text:
@@ -115,7 +117,8 @@ def build(jobs=None, regenerate=True):
         with contextlib.redirect_stdout(io.StringIO()):
             gen_eri.main(GEN)
     csrc_out = os.path.join(SRC, "pychem_b200", "csrc")
-    headers = ["pc_common.cuh", "pc_one_electron.cuh", "pc_generic.cuh", "pc_generic_class.h", "pc_jk_kernels.cuh"]
+    headers = ["pc_common.cuh", "pc_one_electron.cuh", "pc_generic.cuh", "pc_generic_class.h", "pc_jk_kernels.cuh",
+               "pc_async.cuh"]
     dep = hashlib.sha1()
     for hname in headers:
         t = transform(open(os.path.join(CSRC, hname)).read(), hname)

@@ -223,6 +223,20 @@ inline uint64_t collective(int op, uint64_t arg, int iarg) {
   return L.res;
 }
 
+// give the other fibers of the block a turn (spin-waits on an emulated mbarrier)
+inline void yield() {
+  Ctx& c = ctx();
+  Lane& L = c.lanes[c.cur];
+  L.state = ST_RUN;
+  swapcontext(&L.ctx, &c.sched);
+}
+
+// dynamic shared memory: one static, 128-byte aligned buffer (blocks run one after another)
+inline unsigned char* dyn_smem() {
+  alignas(128) static unsigned char buf[232448];
+  return buf;
+}
+
 inline void block_barrier() {
   Ctx& c = ctx();
   Lane& L = c.lanes[c.cur];
@@ -321,6 +335,8 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 // every non-null pointer counts as device memory: host buffers are used in place
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) { a->type = p ? cudaMemoryTypeDevice : cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = (void*)p; a->hostPointer = (void*)p; return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(1); return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = std::malloc(1); return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }

@@ -311,11 +311,21 @@ def test_emu_f_shell_dropin_scf(emu, gold, monkeypatch, tmp_path):
     undo = hf_gpu.install(ns.hartree_fock, one_electron=True)      # Core/Overlap from one_electron_kernel<3> too
     try:
         inp = str(tmp_path / "hf.inp")
-        ref_driver.write_input(inp, "hf", helpers.HYDROGEN_FLUORIDE, "cc-pVTZ")
-        mol = ref_driver.run(inp)
+        ref_driver.write_input(inp, "hf", helpers.HYDROGEN_FLUORIDE, "cc-pVTZ", maxiter=200)
         g = gold("f_shell_ccpvtz.npz")
+        parts = gold("hf_ccpvtz_parts.npz")
+        # The reference's own criterion |dE| < 1e-7 (Data/constants.py:32) leaves ~1e-7 of
+        # path-dependent slack in the energy (its stock run ends 3.4e-8 above the SCF limit, the
+        # device run of round 1 ended 3.2e-8 below it, with integrals equal to 1e-14): both sides
+        # run with the criterion at 1e-11, which pins the SCF limit itself.
+        conv = ns.constants.energy_convergence
+        ns.constants.energy_convergence = float(parts["tight_convergence"])
+        try:
+            mol = ref_driver.run(inp)
+        finally:
+            ns.constants.energy_convergence = conv
         e = mol.States[0].TotalEnergy
-        assert abs(e - float(g["fixed_hf_energy"])) < 1.0e-8
+        assert abs(e - float(parts["energy_tight"])) < 1.0e-8
         assert abs(e - float(g["hf_energy"])) > 1.0e-5
         G = np.asarray(mol.CoulombIntegrals)
         assert np.abs(G.ravel()[::997] - g["fixed_hf_G_sample"]).max() < ERI_TOL
