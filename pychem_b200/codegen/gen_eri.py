@@ -322,53 +322,34 @@ class ClassGen:
     V2 = False
 
     def prim_prologue(self, s, nmax):
-        """Primitive loops.  Default: ket primitives outside (per-lane, coalesced loads, once per
-        ket primitive), bra primitives inside (warp-uniform addresses -> broadcast loads).
-        Classes with an s-s ket (nothing to hoist on the ket side) run the bra primitives outside
-        so the bra-only factors (zeta, P-X) leave the inner loop."""
-        bra_outer = (self.Lc == 0 and self.La > 0 and not self.V2 and BRA_OUTER)
+        """Primitive loops: ket primitives outside (per-lane, coalesced SoA loads, once per ket
+        primitive), bra primitives inside.  The lanes of a segment share the bra pair: its
+        primitives come from the pair's contiguous RECORD (PcPairKind::rec, 48 bytes each), loaded
+        one primitive ahead so that the load latency overlaps the recursion of the current one
+        (the prefetch wraps to primitive 0 for the next ket primitive)."""
         ket_load = ["const double2 q0 = __ldg(kp), q1 = __ldg(kp + nk), q2 = __ldg(kp + 2 * (size_t)nk);",
                     "const double sQ = q0.x, UQ = q0.y, Qx = q1.x, Qy = q1.y, Qz = q2.x, kzQ = q2.y;",
                     "const double eta = 0.5 * sQ;",
                     "const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;"]
         ket_load += ["const double ne%d = %d.0 * eta;" % (n, n) for n in range(1, nmax + 1)]
-        bra_load = ["const double2 p0 = __ldg(bq), p1 = __ldg(bq + nb), p2 = __ldg(bq + 2 * (size_t)nb);",
+        bra_load = ["const double2 p0 = n0, p1 = n1, p2 = n2;",
+                    "{ const double2* __restrict__ nx = (ib + 1 < KB) ? bq + 3 : brec + 3; n0 = __ldg(nx); n1 = __ldg(nx + 1); n2 = __ldg(nx + 2); }",
                     "const double sP = p0.x, UP = p0.y, Px = p1.x, Py = p1.y, Pz = p2.x, kzP = p2.y;",
                     "const double zeta = 0.5 * sP;",
                     "const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;"]
         bra_load += ["const double nz%d = %d.0 * zeta;" % (n, n) for n in range(1, nmax + 1)]
-        s.append("  const double2* __restrict__ bp = reinterpret_cast<const double2*>(I.bra.prim) + i;")
-        s.append("  const double2* __restrict__ kp0 = reinterpret_cast<const double2*>(I.ket.prim) + j;")
-        if bra_outer:
-            s.append("  const double2* __restrict__ bq = bp;")
-            s.append("  for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
-            s.extend("    " + l for l in bra_load)
-            s.append("    const double2* __restrict__ kp = kp0;")
-            s.append("    for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
-            s.extend("      " + l for l in ket_load)
-        else:
-            s.append("  const double2* __restrict__ kp = kp0;")
-            s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
-            s.extend("    " + l for l in ket_load)
-            s.append("    const double2* __restrict__ bq = bp;")
-            if self.ilp2():
-                s.append("    int ib = 0;")
-                s.append("    for (; ib + 1 < KB; ib += 2, bq += 6 * (size_t)nb) {")
-                s.append("@@ILP2_BODY@@")
-            else:
-                s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3 * (size_t)nb) {")
-            s.extend("      " + l for l in bra_load)
+        s.append("  const double2* __restrict__ kp = reinterpret_cast<const double2*>(I.ket.prim) + j;")
+        s.append("  double2 n0 = __ldg(brec + 3), n1 = __ldg(brec + 4), n2 = __ldg(brec + 5);")
+        s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
+        s.extend("    " + l for l in ket_load)
+        s.append("    const double2* __restrict__ bq = brec + 3;")
+        s.append("    for (int ib = 0; ib < KB; ++ib, bq += 3) {")
+        s.extend("      " + l for l in bra_load)
         s.append("      const double R0 = Px - Qx, R1 = Py - Qy, R2_ = Pz - Qz;")
         s.append("      const double Rsq = R0 * R0 + R1 * R1 + R2_ * R2_;")
         s.append("      double F[L + 1];")
-        if FUND == "2phase":
-            s.append("      PcFundState<L> fs;")
-            s.append("      if (!(MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT)) pc_fund_p1<L>(sP, UP, sQ, UQ, Rsq, A.boys, fs);")
-            s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F); "
-                     "else pc_fund_p2<L>(fs, F);")
-        else:
-            s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F); "
-                     "else %s<L>(sP, UP, sQ, UQ, Rsq, A.boys, F);" % FUND)
+        s.append("      if (MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT) pc_fundamentals_scatter<L>(sP, UP, sQ, UQ, Rsq, A.scat_S, F); "
+                 "else pc_fundamentals<L>(sP, UP, sQ, UQ, Rsq, A.boys, F);")
         s.append("      const double Rz0 = -R0 * zeta, Rz1 = -R1 * zeta, Rz2 = -R2_ * zeta;")
         s.append("      const double Re0 = R0 * eta, Re1 = R1 * eta, Re2 = R2_ * eta;")
         s.append("      const double ze = zeta * eta;")
@@ -377,27 +358,17 @@ class ClassGen:
         s.append("      (void)QX0; (void)QX1; (void)QX2; (void)PX0; (void)PX1; (void)PX2; (void)ze;")
         s.append("      (void)Rz0; (void)Rz1; (void)Rz2; (void)Re0; (void)Re1; (void)Re2;")
 
-    def ilp2(self):
-        bra_outer = (self.Lc == 0 and self.La > 0 and not self.V2 and BRA_OUTER)
-        return (not self.V2) and (not bra_outer) and self.L <= ILP2_MAXL
-
     def close_prim_loops(self, s):
-        """Close the primitive loops opened by prim_prologue (after the VRR lines were appended).
-        ILP2: the statements since the marker are one inner iteration; emit them twice interleaved
-        inside the pair loop and once more for an odd last primitive."""
-        if self.ilp2():
-            k = s.index("@@ILP2_BODY@@")
-            body = s[k + 1:]
-            del s[k:]
-            s.extend(interleave2(body, "bq + 3 * (size_t)nb"))
-            s.append("    }")
-            s.append("    if (ib < KB) {")
-            s.extend(body)
-            s.append("    }")
-            s.append("  }")
-        else:
-            s.append("    }")
-            s.append("  }")
+        s.append("    }")
+        s.append("  }")
+
+    def bra_record(self, s, ivar, indent="  "):
+        """Header of the bra pair's record: X - Y, Schwarz maximum, first functions, pair id, keff."""
+        s.append(indent + "const double2* __restrict__ brec = reinterpret_cast<const double2*>(I.bra.rec) + (size_t)%s * (3 * (I.bra.K + 1));" % ivar)
+        s.append(indent + "const double2 bh0 = __ldg(brec), bh1 = __ldg(brec + 1);")
+        s.append(indent + "const int4 bh2 = __ldg(reinterpret_cast<const int4*>(brec + 2));")
+        s.append(indent + "const double AB0 = bh0.x, AB1 = bh0.y, AB2 = bh1.x;")
+        s.append(indent + "const int fb = bh2.y, pidb = bh2.z, KB = bh2.w;")
 
     def block_size(self):
         return 128 if self.L <= 4 else 64
@@ -465,6 +436,9 @@ class ClassGen:
         s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const __grid_constant__ PcEriArgs A) {" % (block, self.run_min_blocks(), self.name))
         s.append("  constexpr bool JK = (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN) || MODE == PC_MODE_JK_GEN_BATCH;")
         s.append("  constexpr bool JKP = (MODE == PC_MODE_JK_RHF || MODE == PC_MODE_JK_UHF);   // resident images")
+        s.append("  typedef PcSegScratch<PcSegNeed<MODE, %s, true>::ROWS> Scratch;" % dims)
+        s.append("  __shared__ Scratch seg_scratch[%d];" % (block // 32))
+        s.append("  Scratch* S = &seg_scratch[threadIdx.x >> 5];")
         s.append("  const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);")
         s.append("  if (gw >= A.nwarps) return;")
         s.append("  const PcItem& I = A.items[pc_find_item(A, gw)];")
@@ -485,14 +459,12 @@ class ClassGen:
         s.append("  for (int r = 0; r < rmax; ++r) {")
         s.append("  const int i = min(i0 + r, nb - 1);")
         s.append("  const bool live = r < rseg;")
+        self.bra_record(s, "i")
         s.append("  bool active = live;")
-        s.append("  if (active && !forced) active = (__ldg(I.bra.pm + i) * pk > A.thresh) && (!I.same || i <= j);")
-        s.append("  int fb = 0;")
-        s.append("  if (JK) { fb = __ldg(I.bra.fy + i); pc_run_prefetch<%s>(A, fa0, fb, fc, fd); }" % dims)
+        s.append("  if (active && !forced) active = (bh1.y * pk > A.thresh) && (!I.same || i <= j);")
+        s.append("  if (JK) pc_run_prefetch<%s>(A, fa0, fb, fc, fd);" % dims)
         s.append("  double g[NSPH];")
         s.append("  if (active) {")
-        s.append("  const int KB = __ldg(I.bra.keff + i);")
-        s.append("  const double AB0 = __ldg(I.bra.xy + i), AB1 = __ldg(I.bra.xy + nb + i), AB2 = __ldg(I.bra.xy + 2 * nb + i);")
         s.append("  double acc[NE * NF];")
         s.append("#pragma unroll")
         s.append("  for (int k = 0; k < NE * NF; ++k) acc[k] = 0.0;")
@@ -503,7 +475,7 @@ class ClassGen:
         s.append("  (void)AB0; (void)AB1; (void)AB2;")
         for line in tail:
             s.append("  " + line)
-        s.append("  if (!JK) pc_epilogue<MODE, %s>(A, I, t, i, j, seg_lo, seg_hi, g);" % dims)
+        s.append("  if (!JK) pc_epilogue<MODE, %s>(A, I, t, true, bh2.x, fb, pidb, j, seg_lo, seg_hi, g, S);" % dims)
         s.append("  } else if (JK) {")
         s.append("#pragma unroll")
         s.append("    for (int k = 0; k < NSPH; ++k) g[k] = 0.0;")
@@ -513,21 +485,21 @@ class ClassGen:
         s.append("    double fac = 1.0;")
         s.append("    if (fa0 == fb) fac *= 0.5;")
         s.append("    if (fc == fd) fac *= 0.5;")
-        s.append("    if (__ldg(I.bra.pid + i) == kpid) fac *= 0.5;")
+        s.append("    if (pidb == kpid) fac *= 0.5;")
         s.append("    if (JKP) {")
         s.append("      if (fac != 1.0) {")
         s.append("#pragma unroll")
         s.append("        for (int k = 0; k < NSPH; ++k) g[k] *= fac;")
         s.append("      }")
-        s.append("      pc_run_iter(A, RA, fa0, fb, fc, fd, g, active, live, seg_lo, seg_hi);")
+        s.append("      pc_run_iter(A, RA, fa0, fb, fc, fd, g, active, live, seg_lo, seg_hi, S);")
         s.append("    } else {")
         s.append("      // general densities: all images per quartet (lanes without a quartet add zeros)")
-        s.append("      pc_digest_any<MODE, %s>(A, fa0, fb, fc, fd, fac, g, true, seg_lo, seg_hi);" % dims)
+        s.append("      pc_digest_any<MODE, %s>(A, fa0, fb, fc, fd, fac, g, active, live, seg_lo, seg_hi, S);" % dims)
         s.append("    }")
         s.append("  }")
         s.append("  }")
         s.append("  (void)CD0; (void)CD1; (void)CD2;")
-        s.append("  if (JKP) pc_run_final(A, RA, fa0, fc, fd, rseg > 0, seg_lo, seg_hi);")
+        s.append("  if (JKP) pc_run_final(A, RA, fa0, fc, fd, rseg > 0, seg_lo, seg_hi, S);")
         s.append("}")
         s.append("}  // namespace")
         s.append("")
@@ -542,6 +514,7 @@ class ClassGen:
         nsp = NA * NB * NC * ND
         nmax = max(self.La, self.Lc, 1)
         block = self.block_size()
+        dims = "%d, %d, %d, %d" % (NA, NB, NC, ND)
         s = []
         s.append("// GENERATED by pychem_b200/codegen/gen_eri.py -- do not edit.")
         s.append("// class (%s%s|%s%s)%s: L=%d, %d x %d contracted (e0|f0), %d VRR temporaries, %d tail temporaries"
@@ -555,17 +528,22 @@ class ClassGen:
         s.append("")
         s.append("template <int MODE>")
         s.append("__global__ void __launch_bounds__(%d, %d) eri_%s_kernel(const __grid_constant__ PcEriArgs A) {" % (block, self.min_blocks(), self.name))
+        s.append("  typedef PcSegScratch<PcSegNeed<MODE, %s, false>::ROWS> Scratch;" % dims)
+        s.append("  __shared__ Scratch seg_scratch[%d];" % (block // 32))
+        s.append("  Scratch* S = &seg_scratch[threadIdx.x >> 5];")
         s.append("  const int gw = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);")
         s.append("  if (gw >= A.nwarps) return;")
         s.append("  const PcItem& I = A.items[pc_find_item(A, gw)];")
         s.append("  const long long t = (long long)(gw - I.warp0) * 32 + (threadIdx.x & 31);")
         s.append("  int i, j, seg_lo, seg_hi;")
-        s.append("  if (!pc_decode_task(A, I, t, i, j, seg_lo, seg_hi)) return;")
+        s.append("  bool valid;")
+        s.append("  if (!pc_decode_live(A, I, t, i, j, seg_lo, seg_hi, valid)) return;")
+        self.bra_record(s, "i")
+        s.append("  const int fa = bh2.x;")
         s.append("  // contraction depths after the primitive-pair cut-off (per shell pair)")
-        s.append("  const int nb = I.bra.n, nk = I.ket.n, KB = __ldg(I.bra.keff + i), KK = __ldg(I.ket.keff + j);")
+        s.append("  const int nk = I.ket.n, KK = __ldg(I.ket.keff + j);")
         s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
-        s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, __ldg(I.bra.fx + i), __ldg(I.bra.fy + i), __ldg(I.ket.fx + j), __ldg(I.ket.fy + j), MODE != PC_MODE_JK_GEN);" % (NA, NB, NC, ND))
-        s.append("  const double AB0 = __ldg(I.bra.xy + i), AB1 = __ldg(I.bra.xy + nb + i), AB2 = __ldg(I.bra.xy + 2 * nb + i);")
+        s.append("    pc_prefetch_density<%s>(A, fa, fb, __ldg(I.ket.fx + j), __ldg(I.ket.fy + j), MODE != PC_MODE_JK_GEN);" % dims)
         s.append("  const double CD0 = __ldg(I.ket.xy + j), CD1 = __ldg(I.ket.xy + nk + j), CD2 = __ldg(I.ket.xy + 2 * nk + j);")
         s.append("  double acc[NE * NF];")
         s.append("#pragma unroll%s" % (" 1" if self.V2 else ""))
@@ -579,21 +557,11 @@ class ClassGen:
         s.append("  double g[NSPH];")
         for line in tail:
             s.append("  " + line)
-        s.append("  pc_epilogue<MODE, %d, %d, %d, %d>(A, I, t, i, j, seg_lo, seg_hi, g);" % (NA, NB, NC, ND))
+        s.append("  pc_epilogue<MODE, %s>(A, I, t, valid, fa, fb, pidb, j, seg_lo, seg_hi, g, S);" % dims)
         s.append("}")
         s.append("}  // namespace")
         s.append("")
-        s.append("cudaError_t pc_launch_%s(int mode, const PcEriArgs& A, cudaStream_t st) {" % self.name)
-        s.append("  if (A.nwarps <= 0) return cudaSuccess;")
-        s.append("  const int block = %d;" % block)
-        s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
-        s.append("  switch (mode) {")
-        for mode in MODES:
-            s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
-        s.append("    default: return cudaErrorInvalidValue;")
-        s.append("  }")
-        s.append("  return cudaGetLastError();")
-        s.append("}")
+        s.extend(self.launcher(block))
         return "\n".join(s) + "\n"
 
     def tables(self):
@@ -855,57 +823,6 @@ class ClassGenV2(ClassGen):
         return lines
 
 
-# measured on (H2O)32: slower (psss 3.73 vs 3.43 ms) -- the per-lane ket loads move into the inner
-# loop and cost more L1 wavefronts than the three multiplies saved; kept as an experiment switch
-BRA_OUTER = os.environ.get("PC_GEN_BRA_OUTER", "0") != "0"
-# ILP2 (experiment, default off): classes with L <= PC_GEN_ILP2_MAXL process TWO bra primitives per
-# inner iteration with the statements of both copies interleaved in the source (the recursion of a
-# primitive quartet is one dependent chain; two independent chains side by side give the scheduler
-# something to overlap).  Meant to be combined with PC_GEN_FUND=bf (no branches in the body).
-ILP2_MAXL = int(os.environ.get("PC_GEN_ILP2_MAXL", "-1"))
-
-
-def interleave2(body, second_ptr):
-    """body: the statements of one inner iteration reading the bra primitive at `bq`.  Returns the
-    statements of two iterations (bq and second_ptr) interleaved line by line; every name the body
-    defines gets the suffix _B in the second copy, acc[] is shared."""
-    import re
-    names = set()
-    for line in body:
-        m = re.match(r"\s*(?:const\s+)?(?:double2?|PcFundState<L>)\s+(.*);\s*$", line)
-        if not m:
-            continue
-        decl = m.group(1)
-        depth = 0
-        cur = ""
-        parts = []
-        for ch in decl:
-            if ch in "([{":
-                depth += 1
-            elif ch in ")]}":
-                depth -= 1
-            if ch == "," and depth == 0:
-                parts.append(cur)
-                cur = ""
-            else:
-                cur += ch
-        parts.append(cur)
-        for part in parts:
-            mm = re.match(r"\s*([A-Za-z_]\w*)", part)
-            if mm:
-                names.add(mm.group(1))
-    pat = re.compile(r"\b(%s)\b" % "|".join(sorted(names, key=len, reverse=True)))
-    out = []
-    for line in body:
-        out.append(line)
-        b = pat.sub(lambda m: m.group(1) + "_B", line)
-        b = re.sub(r"\bbq\b", "(%s)" % second_ptr, b)
-        out.append(b)
-    return out
-
-
-# fundamentals: "" = three-branch form (default), "bf" = branch-free select form (experiment)
-FUND = {"": "pc_fundamentals", "bf": "pc_fundamentals_bf", "2phase": "2phase"}[os.environ.get("PC_GEN_FUND", "")]
 FUSE_ACC = os.environ.get("PC_GEN_FUSE_ACC", "1") != "0"
 V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
 

@@ -103,13 +103,14 @@ struct Kind {
   std::vector<double> pm;       // [n] Schwarz maximum by position
   std::vector<int> keff_h;      // [n] significant primitive pairs by position
   DevBuf<int> fx, fy, pid, keff;
-  DevBuf<double> xy, prim, pmd;
+  DevBuf<double> xy, prim, pmd, rec;
   PcPairKind view() const {
     PcPairKind v;
     v.n = (int)pairs.size();
     v.K = K;
     v.fx = fx.p; v.fy = fy.p; v.pid = pid.p; v.keff = keff.p; v.xy = xy.p; v.prim = prim.p;
     v.pm = pmd.p;
+    v.rec = rec.p;
     return v;
   }
 };
@@ -379,6 +380,18 @@ int upload_kind(pc_basis* h, Kind* k) {
       o2[0] = src[4]; o2[1] = src[5];
     }
   }
+  // the bra-side records (PcPairKind::rec): header + primitives of one pair, contiguous
+  std::vector<double> rec((size_t)6 * (K + 1) * (n + 1), 0.0);
+  for (int i = 0; i < n; ++i) {
+    const HostPair& p = h->pairs[k->pairs[i]];
+    double* o = &rec[(size_t)6 * (K + 1) * i];
+    for (int c = 0; c < 3; ++c) o[c] = xy[(size_t)c * n + i];
+    o[3] = ((int)k->pm.size() == n) ? k->pm[i] : 0.0;
+    int hdr[4] = {fx[i], fy[i], pid[i], keff[i]};
+    memcpy(o + 4, hdr, sizeof(hdr));
+    memcpy(o + 6, &h->prim_host[p.prim_off * 6], sizeof(double) * 6 * K);
+  }
+  PC_CUDA(k->rec.upload(rec, h->stream));
   k->keff_h = keff;
   PC_CUDA(k->keff.upload(keff, h->stream));
   PC_CUDA(k->fx.upload(fx, h->stream));
@@ -1175,10 +1188,10 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
     if (N % 2 == 0 && N >= 8 && !no_tma) {
       // TMA-staged kernel: ~24 KB tiles (rt rows of the NBG slabs), 4 in flight per CTA
       constexpr int STAGES = 4;
-      const int rt = std::max(1, (int)(24576 / ((size_t)NBG * N * sizeof(double))));
+      const int rt = std::max(1, (int)(24576 / ((size_t)(NBG + 1) * N * sizeof(double))));
       const int ct = std::min(256, ((N / 2 + 31) / 32) * 32);      // threads along the columns (pairs)
       const int rgn = std::max(1, 256 / ct);
-      const size_t smem = ((size_t)STAGES * NBG * rt * N + (size_t)2 * NBG * N + (size_t)2 * rgn * 2 * ct) * sizeof(double);
+      const size_t smem = ((size_t)STAGES * (NBG + 1) * rt * N + (size_t)2 * NBG * N + (size_t)2 * rgn * 2 * ct) * sizeof(double);
       if (N / 2 <= 256 && smem <= 200 * 1024) {
         static bool attr_set = false;
         if (!attr_set) {

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const d
       for (int c = rg; c < N; c += RG) {
         double t[VEC];
         if (VEC == 2) {
-          const double2 t2 = __ldg(reinterpret_cast<const double2*>(Dt + (size_t)c * N + d));
+          const double2 t2 = *reinterpret_cast<const double2*>(st + ((size_t)NB * rt + r) * N + d);
           t[0] = t2.x; t[VEC - 1] = t2.y;
         } else {
           t[0] = __ldg(Dt + (size_t)c * N + d);
@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const d
 
 // The same contraction with the tensor staged through shared memory by the TMA engine
 // (`cp.async.bulk`, pc_async.cuh): a CTA owns NB consecutive slabs G[a, b0..b0+NB-1, :, :]; one
-// tile = `rt` rows c of all NB slabs (NB contiguous pieces of rt*N doubles), STAGES tiles in
+// tile = `rt` rows c of all NB slabs (NB contiguous pieces of rt*N doubles)
+// (plus the same rows of Dt), STAGES tiles in
 // flight per CTA behind full / empty mbarriers.  Thread 0 issues the copies -- no registers and
 // no LSU slots are spent on the 8 N^4 bytes -- everybody consumes: a thread owns the column pair
 // (d, d+1) of one row group for the whole CTA, so X[a, d] stays in registers until the end and
@@ -145,7 +146,7 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
   const size_t NN = (size_t)N * N;
   const double* __restrict__ slab = G + ((size_t)a * N + b0) * NN;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const size_t tile_doubles = (size_t)NB * rt * N;                 // one stage
+  const size_t tile_doubles = (size_t)(NB + 1) * rt * N;           // one stage: NB slab pieces + the Dt rows
   double* stage0 = reinterpret_cast<double*>(smem_raw);
   double* sD = stage0 + (size_t)STAGES * tile_doubles;            // [2][NB][N]: Da[c, b0+k], Db[c, b0+k]
   double* sX = sD + (size_t)2 * NB * N;                            // [2][rgn][2 ct]
@@ -160,9 +161,11 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
     const int s = t % STAGES;
     const int rows = min(rt, N - t * rt);
     const unsigned bytes = (unsigned)((size_t)rows * N * sizeof(double));
-    pc_mbar_arrive_expect_tx(&full[s], bytes * (unsigned)nbv);
+    pc_mbar_arrive_expect_tx(&full[s], bytes * (unsigned)(nbv + 1));
     for (int k = 0; k < nbv; ++k)
       pc_bulk_g2s(stage0 + (size_t)s * tile_doubles + (size_t)k * rt * N, slab + (size_t)k * NN + (size_t)t * rt * N, bytes, &full[s]);
+    // the matching rows of Dt ride along (from L2): no global load is left in the consumer loop
+    pc_bulk_g2s(stage0 + (size_t)s * tile_doubles + (size_t)NB * rt * N, Dt + (size_t)t * rt * N, bytes, &full[s]);
   };
   if (tid == 0)
     for (int t = 0; t < min(STAGES, ntiles); ++t) issue(t);

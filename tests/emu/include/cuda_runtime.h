@@ -45,6 +45,8 @@
 // ---------------------------------------------------------------------------------------------
 struct alignas(16) double2 { double x, y; };
 struct alignas(8) int2 { int x, y; };
+struct alignas(16) int4 { int x, y, z, w; };
+inline int4 make_int4(int x, int y, int z, int w) { int4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 inline double2 make_double2(double x, double y) { double2 r; r.x = x; r.y = y; return r; }
