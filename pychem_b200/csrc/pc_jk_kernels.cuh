@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const d
       for (int c = rg; c < N; c += RG) {
         double t[VEC];
         if (VEC == 2) {
-          const double2 t2 = *reinterpret_cast<const double2*>(st + ((size_t)NB * rt + r) * N + d);
+          const double2 t2 = __ldg(reinterpret_cast<const double2*>(Dt + (size_t)c * N + d));
           t[0] = t2.x; t[VEC - 1] = t2.y;
         } else {
           t[0] = __ldg(Dt + (size_t)c * N + d);
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
       const double* __restrict__ st = stage0 + (size_t)s * tile_doubles;
       for (int r = rgi; r < rows; r += rgn) {
         const int c = t * rt + r;
-        const double2 t2 = __ldg(reinterpret_cast<const double2*>(Dt + (size_t)c * N + d));
+        const double2 t2 = *reinterpret_cast<const double2*>(st + ((size_t)NB * rt + r) * N + d);
 #pragma unroll
         for (int k = 0; k < NB; ++k) {
           // slabs beyond the tensor (k >= nbv) were never copied: their density factors are 0 and
