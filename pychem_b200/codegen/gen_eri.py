@@ -332,14 +332,19 @@ class ClassGen:
                     "const double eta = 0.5 * sQ;",
                     "const double QX0 = -CD0 * kzQ, QX1 = -CD1 * kzQ, QX2 = -CD2 * kzQ;"]
         ket_load += ["const double ne%d = %d.0 * eta;" % (n, n) for n in range(1, nmax + 1)]
-        bra_load = ["const double2 p0 = n0, p1 = n1, p2 = n2;",
-                    "{ const double2* __restrict__ nx = (ib + 1 < KB) ? bq + 3 : brec + 3; n0 = __ldg(nx); n1 = __ldg(nx + 1); n2 = __ldg(nx + 2); }",
+        if PREFETCH == 1:
+            bra_load = ["const double2 p0 = n0, p1 = n1, p2 = n2;",
+                        "{ const double2* __restrict__ nx = (ib + 1 < KB) ? bq + 3 : brec + 3; n0 = __ldg(nx); n1 = __ldg(nx + 1); n2 = __ldg(nx + 2); }"]
+        else:
+            bra_load = ["const double2 p0 = __ldg(bq), p1 = __ldg(bq + 1), p2 = __ldg(bq + 2);"]
+        bra_load += [
                     "const double sP = p0.x, UP = p0.y, Px = p1.x, Py = p1.y, Pz = p2.x, kzP = p2.y;",
                     "const double zeta = 0.5 * sP;",
                     "const double PX0 = -AB0 * kzP, PX1 = -AB1 * kzP, PX2 = -AB2 * kzP;"]
         bra_load += ["const double nz%d = %d.0 * zeta;" % (n, n) for n in range(1, nmax + 1)]
         s.append("  const double2* __restrict__ kp = reinterpret_cast<const double2*>(I.ket.prim) + j;")
-        s.append("  double2 n0 = __ldg(brec + 3), n1 = __ldg(brec + 4), n2 = __ldg(brec + 5);")
+        if PREFETCH == 1:
+            s.append("  double2 n0 = __ldg(brec + 3), n1 = __ldg(brec + 4), n2 = __ldg(brec + 5);")
         s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
         s.extend("    " + l for l in ket_load)
         s.append("    const double2* __restrict__ bq = brec + 3;")
@@ -369,6 +374,9 @@ class ClassGen:
         s.append(indent + "const int4 bh2 = __ldg(reinterpret_cast<const int4*>(brec + 2));")
         s.append(indent + "const double AB0 = bh0.x, AB1 = bh0.y, AB2 = bh1.x;")
         s.append(indent + "const int fb = bh2.y, pidb = bh2.z, KB = bh2.w;")
+        if PREFETCH == 2:
+            # the rest of the record (48 (K + 1) bytes from brec) into L1 while the ket side is loaded
+            s.append(indent + "for (int ln = 128; ln < 48 * (KB + 1); ln += 128) pc_prefetch_l1(reinterpret_cast<const char*>(brec) + ln);")
 
     def block_size(self):
         return 128 if self.L <= 4 else 64
@@ -823,6 +831,9 @@ class ClassGenV2(ClassGen):
         return lines
 
 
+# bra-record prefetch: 0 = none (the record's lines hit L1 after the first touch), 1 = next primitive
+# one iteration ahead in registers, 2 = prefetch.global.L1 of the record's lines at task start
+PREFETCH = int(os.environ.get("PC_GEN_PREFETCH", "0"))
 FUSE_ACC = os.environ.get("PC_GEN_FUSE_ACC", "1") != "0"
 V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
 
