@@ -597,15 +597,20 @@ def stored_mode_leg(torch, engine, S, dev, args):
     Da = torch.from_numpy(0.5 * (X + X.T)).to(dev)
     Dt = 2.0 * Da
     torch.cuda.synchronize()
-    for _ in range(3):
-        db.jk_stored(G_dev, Dt, Da, Da)
     reps = 20
-    e0.record(stream)
-    for _ in range(reps):
-        db.jk_stored(G_dev, Dt, Da, Da)
-    e1.record(stream)
-    e1.synchronize()
-    jk_ms = e0.elapsed_time(e1) / reps
+    kernels = {}
+    for name, flag in (("tma_pipeline", "1"), ("ldg128", "0")):       # the default (ldg128) last
+        os.environ["PYCHEM_B200_STORED_TMA"] = flag
+        for _ in range(3):
+            db.jk_stored(G_dev, Dt, Da, Da)
+        e0.record(stream)
+        for _ in range(reps):
+            db.jk_stored(G_dev, Dt, Da, Da)
+        e1.record(stream)
+        e1.synchronize()
+        kernels[name] = e0.elapsed_time(e1) / reps
+    os.environ.pop("PYCHEM_B200_STORED_TMA", None)
+    jk_ms = kernels["ldg128"]
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         src = "MEASURED_PEAKS.json hbm_gbs"
@@ -614,6 +619,8 @@ def stored_mode_leg(torch, engine, S, dev, args):
     gbs = 8.0 * N ** 4 / (jk_ms * 1e-3) / 1e9
     out = {"workload": "(H2O)8 6-31G** stored-tensor mode, N=%d, tensor %.1f GB" % (N, 8.0 * N ** 4 / 1e9),
            "tensor_build_ms": tensor_ms, "jk_ms": jk_ms,
+           "kernels_ms": {"jk_stored_kernel (16-byte loads, default)": kernels["ldg128"],
+                          "jk_stored_tma_kernel (cp.async.bulk + mbarrier pipeline, PYCHEM_B200_STORED_TMA=1)": kernels["tma_pipeline"]},
            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
                         "algorithmic_bytes": 8.0 * N ** 4, "peak_source": src,
                         "note": "one streaming pass over the tensor per Fock build (the reference's three einsum passes read 24 N^4 bytes); "

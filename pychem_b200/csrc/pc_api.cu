@@ -1184,9 +1184,14 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
   {
     constexpr int NBG = 4;                       // slabs per CTA
     const int ngrp = (N + NBG - 1) / NBG;
-    static const bool no_tma = getenv("PYCHEM_B200_STORED_NO_TMA") != nullptr;      // A/B switch
-    if (N % 2 == 0 && N >= 8 && !no_tma) {
-      // TMA-staged kernel: ~24 KB tiles (rt rows of the NBG slabs), 4 in flight per CTA
+    // Two kernels stream the tensor (profiles/r2c_stored_mode.txt, N = 192, 10.9 GB): plain 16-byte
+    // loads reach 99 % of the measured HBM copy bandwidth, the TMA-staged pipeline 95 %; both
+    // needed the per-CTA rotated order (66 % without).  Default: the faster one;
+    // PYCHEM_B200_STORED_TMA=1 selects the TMA pipeline (read per call: bench.py times both).
+    const char* tma_env = getenv("PYCHEM_B200_STORED_TMA");
+    const bool use_tma = tma_env && atoi(tma_env) != 0;
+    if (N % 2 == 0 && N >= 8 && use_tma) {
+      // TMA-staged kernel: ~24 KB tiles (rt rows of the NBG slabs + Dt), 4 in flight per CTA
       constexpr int STAGES = 4;
       const int rt = std::max(1, (int)(24576 / ((size_t)(NBG + 1) * N * sizeof(double))));
       const int ct = std::min(256, ((N / 2 + 31) / 32) * 32);      // threads along the columns (pairs)
@@ -1198,7 +1203,7 @@ int pc_jk_stored(pc_basis* h, const double* G_dev, const double* Dt, const doubl
           PC_CUDA(cudaFuncSetAttribute(jk_stored_tma_kernel<NBG, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
           attr_set = true;
         }
-        jk_stored_tma_kernel<NBG, STAGES><<<N * ngrp, 256, smem, h->stream>>>(N, ngrp, rt, ct, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
+        jk_stored_tma_kernel<NBG, STAGES><<<N * ngrp, 288, smem, h->stream>>>(N, ngrp, rt, ct, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
       } else {
         jk_stored_kernel<2, NBG><<<N * ngrp, 256, 0, h->stream>>>(N, ngrp, G_dev, dt, da, db, o, o + nn, o + 2 * nn);
       }

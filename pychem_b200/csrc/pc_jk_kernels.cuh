@@ -127,13 +127,13 @@ __global__ void __launch_bounds__(256) jk_stored_kernel(int N, int ngrp, const d
 // (`cp.async.bulk`, pc_async.cuh): a CTA owns NB consecutive slabs G[a, b0..b0+NB-1, :, :]; one
 // tile = `rt` rows c of all NB slabs (NB contiguous pieces of rt*N doubles)
 // (plus the same rows of Dt), STAGES tiles in
-// flight per CTA behind full / empty mbarriers.  Thread 0 issues the copies -- no registers and
-// no LSU slots are spent on the 8 N^4 bytes -- everybody consumes: a thread owns the column pair
+// flight per CTA behind full / empty mbarriers.  A producer warp issues the copies -- no registers and
+// no LSU slots are spent on the 8 N^4 bytes -- eight warps consume: a thread owns the column pair
 // (d, d+1) of one row group for the whole CTA, so X[a, d] stays in registers until the end and
 // the row groups meet once, in shared memory.  Needs N even (16-byte rows); odd N keeps
 // jk_stored_kernel.  Dynamic shared memory: stage buffers | Da/Db columns | reduction scratch.
 template <int NB, int STAGES>
-__global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int rt, int ct,
+__global__ void __launch_bounds__(288) jk_stored_tma_kernel(int N, int ngrp, int rt, int ct,
                                                             const double* __restrict__ G,
                                                             const double* __restrict__ Dt,
                                                             const double* __restrict__ Da,
@@ -148,7 +148,10 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
   const int nbv = min(NB, N - b0);
   const size_t NN = (size_t)N * N;
   const double* __restrict__ slab = G + ((size_t)a * N + b0) * NN;
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  // 8 consumer warps + 1 producer warp (its first lane issues the bulk copies and never computes,
+  // so a refill is not held up by the issuing thread's own share of the previous tile)
+  const int tid = threadIdx.x, nthr = 256;
+  const bool producer = tid >= 256;
   const size_t tile_doubles = (size_t)(NB + 1) * rt * N;           // one stage: NB slab pieces + the Dt rows
   double* stage0 = reinterpret_cast<double*>(smem_raw);
   double* sD = stage0 + (size_t)STAGES * tile_doubles;            // [2][NB][N]: Da[c, b0+k], Db[c, b0+k]
@@ -176,24 +179,31 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
     // the matching rows of Dt ride along (from L2): no global load is left in the consumer loop
     pc_bulk_g2s(stage0 + (size_t)s * tile_doubles + (size_t)NB * rt * N, Dt + (size_t)t * rt * N, bytes, &full[s]);
   };
-  if (tid == 0)
-    for (int t = 0; t < min(STAGES, ntiles); ++t) issue(t);
+  if (tid == 256)
+    for (int tl = 0; tl < min(STAGES, ntiles); ++tl) issue(tl);
   // the density columns this CTA needs for the exchange part
-  for (int idx = tid; idx < N * NB; idx += nthr) {
+  for (int idx = tid; idx < N * NB && !producer; idx += nthr) {
     const int c = idx / NB, k = idx % NB;
     const bool ok = k < nbv;
     sD[(size_t)k * N + c] = ok ? __ldg(Da + (size_t)c * N + b0 + k) : 0.0;
     sD[(size_t)(NB + k) * N + c] = ok ? __ldg(Db + (size_t)c * N + b0 + k) : 0.0;
   }
   __syncthreads();
+  if (tid == 256) {
+    for (int tl = STAGES; tl < ntiles; ++tl) {
+      // the k-th use of a stage waits until the consumers have left its (k-1)-th tile
+      pc_mbar_wait(&empty[tl % STAGES], (unsigned)((tl / STAGES - 1) & 1));
+      issue(tl);
+    }
+  }
   const int rgn = nthr / ct;                                       // row groups
   const int cg = tid % ct, rgi = tid / ct;
   const int d = 2 * cg;
-  const bool active = d < N && rgi < rgn;
+  const bool active = d < N && rgi < rgn && !producer;
   double jsum[NB], xa0 = 0.0, xa1 = 0.0, xb0 = 0.0, xb1 = 0.0;
 #pragma unroll
   for (int k = 0; k < NB; ++k) jsum[k] = 0.0;
-  for (int tl = 0; tl < ntiles; ++tl) {
+  for (int tl = 0; tl < ntiles && !producer; ++tl) {
     const int s = tl % STAGES;
     const int t = (tl + t0) % ntiles;
     pc_mbar_wait(&full[s], (unsigned)((tl / STAGES) & 1));
@@ -219,20 +229,14 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
       }
     }
     pc_mbar_arrive(&empty[s]);
-    // refill the stage of the PREVIOUS tile: by now everybody has normally left it
-    if (tid == 0 && tl >= 1 && tl - 1 + STAGES < ntiles) {
-      const int sp = (tl - 1) % STAGES;
-      pc_mbar_wait(&empty[sp], (unsigned)(((tl - 1) / STAGES) & 1));
-      issue(tl - 1 + STAGES);
-    }
   }
   // ---- exchange: sum the row groups, one atomic per column (the ngrp CTAs of row a meet here)
-  if (rgi < rgn) {
+  if (rgi < rgn && !producer) {
     sX[((size_t)0 * rgn + rgi) * 2 * ct + 2 * cg] = xa0; sX[((size_t)0 * rgn + rgi) * 2 * ct + 2 * cg + 1] = xa1;
     sX[((size_t)1 * rgn + rgi) * 2 * ct + 2 * cg] = xb0; sX[((size_t)1 * rgn + rgi) * 2 * ct + 2 * cg + 1] = xb1;
   }
   __syncthreads();
-  for (int idx = tid; idx < 2 * N; idx += nthr) {
+  for (int idx = tid; idx < 2 * N && !producer; idx += nthr) {
     const int which = idx / N, col = idx % N;
     double sum = 0.0;
     for (int g = 0; g < rgn; ++g) sum += sX[((size_t)which * rgn + g) * 2 * ct + col];
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(256) jk_stored_tma_kernel(int N, int ngrp, int
   for (int k = 0; k < NB; ++k) {
     double v = active ? jsum[k] : 0.0;
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) jred[w][k] = v;
+    if (lane == 0 && !producer) jred[w][k] = v;
   }
   __syncthreads();
   if (tid < nbv) {
