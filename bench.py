@@ -420,8 +420,9 @@ def run_b200(args):
     def e2e_run(pinned):
         if pinned:
             Dt_p, Da_p = torch.from_numpy(main.Dt_h).pin_memory(), torch.from_numpy(main.Da_h).pin_memory()
-            state = _State(Dt_p.numpy(), Da_p.numpy(), Da_p.numpy().copy())
-            state._keep = (Dt_p, Da_p)
+            Db_p = torch.from_numpy(main.Da_h).pin_memory()
+            state = _State(Dt_p.numpy(), Da_p.numpy(), Db_p.numpy())        # three distinct pinned arrays
+            state._keep = (Dt_p, Da_p, Db_p)
         else:
             # what the reference's SCF driver hands over: three distinct pageable numpy arrays
             state = _State(main.Dt_h.copy(), main.Da_h.copy(), main.Da_h.copy())
@@ -560,9 +561,9 @@ def run_b200(args):
                 "eri_generation_only": {"ms_per_pass": eri_only_ms, "value": counts["all_eris"] / (eri_only_ms * 1e-3), "unit": UNIT},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": 3 * N * N * 8, "d2h_bytes_per_step": 3 * N * N * 8,
-                        "call": "pychem_b200.hartree_fock.make_coulomb_exchange_matrices(molecule, state), pinned host "
-                                "densities in, J / X host arrays out",
+                        "h2d_bytes_per_step": 3 * N * N * 8, "d2h_bytes_per_step": 2 * N * N * 8,
+                        "call": "pychem_b200.hartree_fock.make_coulomb_exchange_matrices(molecule, state), three pinned host "
+                                "densities in, J / X host arrays out (closed-shell result: X_beta is the X_alpha array, 2 N^2 doubles back)",
                         "pageable_inputs": {"ms_per_step": e2e_page_ms, "value": counts["all_eris"] / (e2e_page_ms * 1e-3),
                                             "note": "three distinct pageable numpy arrays, as the reference's SCF driver passes"}},
                 "gpu_launches": int(launches),

@@ -127,6 +127,11 @@ int pc_jk_finalize(pc_basis* h, int variant, const double* acc_dev, double* J, d
  * receives the variant that was used (pass it to pc_jk_finalize). */
 int pc_jk_direct_accumulate_auto(pc_basis* h, const double* Dt, const double* Da, const double* Db,
                                  double* acc_dev, int* variant);
+/* pc_jk_direct with the variant picked on the device and reported in *variant.  When the densities
+ * turn out closed-shell (PC_JK_RHF: symmetric, Da == Db) X_beta equals X_alpha and Xb is NOT
+ * written: the caller aliases it (one device->host copy less per Fock build). */
+int pc_jk_direct_auto(pc_basis* h, const double* Dt, const double* Da, const double* Db, double* J,
+                      double* Xa, double* Xb, int* variant);
 int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
                  double* J, double* Xa, double* Xb);
 /* variant (PC_JK_RHF/UHF/GEN) the densities allow: symmetric & Da==Db / symmetric / general.
@@ -192,6 +197,8 @@ int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, cons
                   double* Eab, double* Ebb);
 const char* pc_mp2_last_error(void);
 /* C (M x N) = A (M x K) . B (K x N), row-major device buffers, through the same DMMA kernel. */
+/* frees the device scratch pc_mp2_energy keeps between calls (four transform intermediates) */
+int pc_mp2_release(void);
 int pc_dgemm_dmma(int device, int M, int N, int K, const double* A, const double* B, double* C);
 
 /*

@@ -32,6 +32,7 @@ SIGNATURES = {
     "pc_jk_finalize": [c_vp, ctypes.c_int] + [c_vp] * 4,
     "pc_jk_direct_accumulate_auto": [c_vp, c_vp, c_vp, c_vp, c_vp, c_ip],
     "pc_jk_direct": [c_vp, ctypes.c_int] + [c_vp] * 6,
+    "pc_jk_direct_auto": [c_vp] + [c_vp] * 6 + [c_ip],
     "pc_jk_classify": [c_vp, c_vp, c_vp, c_vp, c_ip],
     "pc_jk_stored_batch": [c_vp, c_vp, ctypes.c_int, c_vp, c_vp],
     "pc_jk_direct_batch": [c_vp, ctypes.c_int, c_vp, c_vp],
@@ -47,6 +48,7 @@ SIGNATURES = {
     "pc_mp2_energy": [ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, ctypes.c_int,
                       ctypes.c_int, c_dp, c_dp, c_dp],
     "pc_mp2_last_error": [],
+    "pc_mp2_release": [],
     "pc_dgemm_dmma": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp],
 }
 

@@ -8,6 +8,7 @@ the Python that loads it, `install.sh:1-3`), with nvcc instead of distutils:
        nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3
      (objects are cached by source hash, compiled in parallel)
   3. objects are linked into pychem_b200/libpychem_b200.so (git-ignored, shipped with the snapshot)
+  4. pychem_b200/setup_c_ints.py (setuptools Extension) builds the host-side `_c_ints` module
 """
 import hashlib
 import os
@@ -70,6 +71,10 @@ def build(verbose=False, jobs=None):
     with ThreadPoolExecutor(jobs) as ex:
         res = list(ex.map(lambda s: _compile(s, api_deps if (s.endswith("pc_api.cu") or s.endswith("pc_mp2.cu")) else
                                               (gen_deps if s.endswith("pc_generic.cu") else deps), verbose), srcs))
+    # the host-side `_c_ints` module (legacy entry points), built like the reference's own extension
+    sys.path.insert(0, HERE)
+    import setup_c_ints
+    setup_c_ints.build_inplace()
     objs = [o for o, _ in res]
     if any(changed for _, changed in res) or not os.path.exists(LIB):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs

@@ -8,6 +8,7 @@
 #include "pc_one_electron.cuh"
 #include "pc_generic_class.h"
 #include "pc_jk_kernels.cuh"
+#include "pc_boys_table.h"
 
 #include <algorithm>
 #include <atomic>
@@ -154,35 +155,9 @@ bool is_device_ptr(const void* p) {
 // Boys table: cubic in sT = T/(2d) per interval, third-order Taylor about the interval centre
 // (consumer: Methods/c_ints/two_electron_fundamentals.c:62-75; table blob missing upstream)
 // ------------------------------------------------------------------------------------------
-void boys_exact(int mmax, long double T, long double* F) {
-  long double term = 1.0L / (2 * mmax + 1), acc = term;
-  for (int k = 1; k < 1000; ++k) {
-    term *= (2 * T) / (2 * mmax + 2 * k + 1);
-    acc += term;
-    if (term < 1e-24L * acc) break;
-  }
-  const long double eT = expl(-T);
-  F[mmax] = eT * acc;
-  for (int m = mmax; m > 0; --m) F[m - 1] = (2 * T * F[m] + eT) / (2 * m - 1);
-}
-
 std::vector<double> make_boys_table() {
   std::vector<double> tab((size_t)PC_BOYS_NM * PC_BOYS_NPOINTS * 4);
-  const long double h = 2.0L * 0.002L;
-  long double F[PC_BOYS_NM + 4];
-  for (int j = 0; j < PC_BOYS_NPOINTS; ++j) {
-    const long double a = j + 0.5L;
-    boys_exact(PC_BOYS_NM + 3, a * h, F);
-    for (int m = 0; m < PC_BOYS_NM; ++m) {
-      const long double c0 = F[m], c1 = -F[m + 1], c2 = F[m + 2] / 2, c3 = -F[m + 3] / 6;
-      const long double h2 = h * h, h3 = h2 * h;
-      double* o = &tab[((size_t)m * PC_BOYS_NPOINTS + j) * 4];
-      o[0] = (double)(c0 - c1 * h * a + c2 * h2 * a * a - c3 * h3 * a * a * a);
-      o[1] = (double)(c1 * h - 2 * c2 * h2 * a + 3 * c3 * h3 * a * a);
-      o[2] = (double)(c2 * h2 - 3 * c3 * h3 * a);
-      o[3] = (double)(c3 * h3);
-    }
-  }
+  pcb_make_table(PC_BOYS_NM, tab.data());          // csrc/pc_boys_table.h (shared with the _c_ints shim)
   return tab;
 }
 
@@ -1413,6 +1388,22 @@ int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, c
   }
   if (pc_jk_direct_accumulate(h, variant, Dt, Da, Db, h->acc.p)) return 1;
   return pc_jk_finalize(h, variant, h->acc.p, J, Xa, Xb);
+}
+
+int pc_jk_direct_auto(pc_basis* h, const double* Dt, const double* Da, const double* Db, double* J,
+                      double* Xa, double* Xb, int* variant) {
+  if (!h || !variant) return fail("pc_jk_direct_auto: null");
+  PC_CUDA(cudaSetDevice(h->device));
+  if (ensure_scratch(h)) return 1;
+  // classify on the device, then digest straight from the staged copies (one upload only)
+  if (pc_jk_classify(h, Dt, Da, Db, variant)) return 1;
+  const size_t nn = (size_t)h->nbf * h->nbf;
+  if (!is_device_ptr(Dt)) Dt = h->dstage.p;
+  if (!is_device_ptr(Da)) Da = h->dstage.p + nn;
+  if (Db && !is_device_ptr(Db)) Db = h->dstage.p + 2 * nn;
+  if (pc_jk_direct_accumulate(h, *variant, Dt, Da, Db, h->acc.p)) return 1;
+  // closed-shell densities: X_beta == X_alpha, nothing is copied into Xb
+  return pc_jk_finalize(h, *variant, h->acc.p, J, Xa, *variant == PC_JK_RHF ? nullptr : Xb);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdint>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -31,54 +33,97 @@ int mp2_fail(const std::string& m) { g_mp2_err = m; return 1; }
     if (e_ != cudaSuccess) return mp2_fail(std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
-constexpr int TM = 64, TN = 64, TK = 16;
+constexpr int TK = 16;
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool ok) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int bytes = ok ? 8 : 0;                         // 0: the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // C[b] (M x N, row-major, ldc) = A[b] (M x K, element (r,k) at A[r*sar + k*sak]) . B[b] (K x N, row-major, ldb)
+// 4 warps laid out WARPS_M x WARPS_N, every warp owns (8 WM) x (8 WN) of C as WM x WN DMMA tiles
+// (mma.sync m8n8k4 f64 -- the only FP64 tensor shape sm_100a has in hardware: the PTX m16n8k8/k16
+// forms lower to the same DMMA.8x8x4, cuobjdump).  Operand tiles are double-buffered in shared
+// memory with cp.async (zero-filled at the edges), so the loads of step k+1 overlap the DMMAs of
+// step k.  The host picks the tile shape that wastes the least padding on the (skinny) MP2 shapes.
+template <int WARPS_M, int WARPS_N, int WM, int WN, bool VEC16>
 __global__ void __launch_bounds__(128) dgemm_dmma_kernel(int M, int N, int K, const double* __restrict__ A,
                                                          long long sar, long long sak, long long batch_a,
                                                          const double* __restrict__ B, long long ldb,
                                                          long long batch_b, double* __restrict__ C,
                                                          long long ldc, long long batch_c) {
-  __shared__ double As[TM][TK + 1];
-  __shared__ double Bs[TK][TN + 8];
+  constexpr int TM = WARPS_M * 8 * WM, TN = WARPS_N * 8 * WN;
+  __shared__ __align__(16) double As[2][TM][TK + 1];
+  __shared__ __align__(16) double Bs[2][TK][TN + 8];
   const int bz = blockIdx.z;
   A += (size_t)bz * batch_a;
   B += (size_t)bz * batch_b;
   C += (size_t)bz * batch_c;
   const int row0 = blockIdx.y * TM, col0 = blockIdx.x * TN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;      // warp tile origin inside the CTA tile
+  const int wr = (warp / WARPS_N) * 8 * WM, wc = (warp % WARPS_N) * 8 * WN;   // warp tile origin
   const int g = lane >> 2, t4 = lane & 3;
-  double acc[4][4][2];
+  double acc[WM][WN][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < WM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int k0 = 0; k0 < K; k0 += TK) {
-    // stage A tile (64 x 16) and B tile (16 x 64), zero-padded at the edges
+  auto stage = [&](int buf, int k0) {
     for (int e = tid; e < TM * TK; e += 128) {
       const int r = e / TK, k = e % TK;
       const int gr = row0 + r, gk = k0 + k;
-      As[r][k] = (gr < M && gk < K) ? A[(size_t)gr * sar + (size_t)gk * sak] : 0.0;
+      const bool ok = gr < M && gk < K;
+      cp_async8(&As[buf][r][k], ok ? A + (size_t)gr * sar + (size_t)gk * sak : A, ok);
     }
-    for (int e = tid; e < TK * TN; e += 128) {
-      const int k = e / TN, c = e % TN;
-      const int gk = k0 + k, gc = col0 + c;
-      Bs[k][c] = (gk < K && gc < N) ? B[(size_t)gk * ldb + gc] : 0.0;
+    if (VEC16) {
+      for (int e = tid; e < TK * (TN / 2); e += 128) {
+        const int k = e / (TN / 2), c = (e % (TN / 2)) * 2;
+        const int gk = k0 + k, gc = col0 + c;
+        const int nbytes = (gk < K && gc < N) ? (gc + 1 < N ? 16 : 8) : 0;
+        cp_async16(&Bs[buf][k][c], nbytes ? B + (size_t)gk * ldb + gc : B, nbytes);
+      }
+    } else {
+      for (int e = tid; e < TK * TN; e += 128) {
+        const int k = e / TN, c = e % TN;
+        const int gk = k0 + k, gc = col0 + c;
+        const bool ok = gk < K && gc < N;
+        cp_async8(&Bs[buf][k][c], ok ? B + (size_t)gk * ldb + gc : B, ok);
+      }
+    }
+    cp_async_commit();
+  };
+
+  const int nk = (K + TK - 1) / TK;
+  stage(0, 0);
+  for (int ks = 0; ks < nk; ++ks) {
+    const int buf = ks & 1;
+    if (ks + 1 < nk) {
+      stage(buf ^ 1, (ks + 1) * TK);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < TK; kk += 4) {
-      double a[4], b[4];
+      double a[WM], b[WN];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[wr + i * 8 + g][kk + t4];
+      for (int i = 0; i < WM; ++i) a[i] = As[buf][wr + i * 8 + g][kk + t4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk + t4][wc + j * 8 + g];
+      for (int j = 0; j < WN; ++j) b[j] = Bs[buf][kk + t4][wc + j * 8 + g];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < WM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < WN; ++j)
           asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                        : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
                        : "d"(a[i]), "d"(b[j]));
@@ -86,9 +131,9 @@ __global__ void __launch_bounds__(128) dgemm_dmma_kernel(int M, int N, int K, co
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < WM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < WN; ++j) {
       const int r = row0 + wr + i * 8 + g;
       const int c = col0 + wc + j * 8 + t4 * 2;
       if (r < M) {
@@ -98,17 +143,47 @@ __global__ void __launch_bounds__(128) dgemm_dmma_kernel(int M, int N, int K, co
     }
 }
 
+struct TileCfg { int tm, tn; };
+constexpr TileCfg kCfg[5] = {{64, 64}, {24, 128}, {80, 64}, {40, 128}, {24, 96}};
+
+template <int WARPS_M, int WARPS_N, int WM, int WN>
+int launch_cfg(cudaStream_t st, bool vec, dim3 grid, int M, int N, int K, const double* A, long long sar, long long sak,
+               long long batch_a, const double* B, long long ldb, long long batch_b, double* C, long long ldc,
+               long long batch_c) {
+  if (vec) dgemm_dmma_kernel<WARPS_M, WARPS_N, WM, WN, true><<<grid, 128, 0, st>>>(M, N, K, A, sar, sak, batch_a, B, ldb, batch_b, C, ldc, batch_c);
+  else dgemm_dmma_kernel<WARPS_M, WARPS_N, WM, WN, false><<<grid, 128, 0, st>>>(M, N, K, A, sar, sak, batch_a, B, ldb, batch_b, C, ldc, batch_c);
+  MP2_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int gemm(cudaStream_t st, int M, int N, int K, const double* A, long long sar, long long sak,
          long long batch_a, const double* B, long long ldb, long long batch_b, double* C, long long ldc,
          long long batch_c, int batches) {
   if (M <= 0 || N <= 0 || K <= 0 || batches <= 0) return 0;
+  // tile shape with the least padded work
+  int best = 0;
+  double best_w = 1e300;
+  for (int c = 0; c < 5; ++c) {
+    const double w = (double)((M + kCfg[c].tm - 1) / kCfg[c].tm) * kCfg[c].tm * (double)((N + kCfg[c].tn - 1) / kCfg[c].tn) * kCfg[c].tn;
+    if (w < best_w * 0.999) { best_w = w; best = c; }
+  }
+  // 16-byte cp.async for B needs 16-byte aligned rows in every batch
+  const bool vec = ((uintptr_t)B % 16 == 0) && (ldb % 2 == 0) && (batch_b % 2 == 0);
   for (int b0 = 0; b0 < batches; b0 += 65535) {
     const int nb = std::min(65535, batches - b0);
-    dim3 grid((N + TN - 1) / TN, (M + TM - 1) / TM, nb);
-    dgemm_dmma_kernel<<<grid, 128, 0, st>>>(M, N, K, A + (size_t)b0 * batch_a, sar, sak, batch_a,
-                                            B + (size_t)b0 * batch_b, ldb, batch_b,
-                                            C + (size_t)b0 * batch_c, ldc, batch_c);
-    MP2_CUDA(cudaGetLastError());
+    dim3 grid((N + kCfg[best].tn - 1) / kCfg[best].tn, (M + kCfg[best].tm - 1) / kCfg[best].tm, nb);
+    const double* Ab = A + (size_t)b0 * batch_a;
+    const double* Bb = B + (size_t)b0 * batch_b;
+    double* Cb = C + (size_t)b0 * batch_c;
+    int rc = 0;
+    switch (best) {
+      case 0: rc = launch_cfg<2, 2, 4, 4>(st, vec, grid, M, N, K, Ab, sar, sak, batch_a, Bb, ldb, batch_b, Cb, ldc, batch_c); break;
+      case 1: rc = launch_cfg<1, 4, 3, 4>(st, vec, grid, M, N, K, Ab, sar, sak, batch_a, Bb, ldb, batch_b, Cb, ldc, batch_c); break;
+      case 2: rc = launch_cfg<2, 2, 5, 4>(st, vec, grid, M, N, K, Ab, sar, sak, batch_a, Bb, ldb, batch_b, Cb, ldc, batch_c); break;
+      case 3: rc = launch_cfg<1, 4, 5, 4>(st, vec, grid, M, N, K, Ab, sar, sak, batch_a, Bb, ldb, batch_b, Cb, ldc, batch_c); break;
+      default: rc = launch_cfg<1, 4, 3, 3>(st, vec, grid, M, N, K, Ab, sar, sak, batch_a, Bb, ldb, batch_b, Cb, ldc, batch_c); break;
+    }
+    if (rc) return rc;
   }
   return 0;
 }
@@ -147,16 +222,40 @@ __global__ void mp2_opp_spin_kernel(int noa, int nva, int nob, int nvb, const do
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
-struct StreamGuard {
+// Scratch of the transform, kept between calls (grow-only, per process): the four intermediates of
+// benzene are 150 MB, allocating and freeing them took longer than the GEMMs (round 1: 17 ms per
+// MP2 energy against ~3 ms of kernels).
+struct Pool {
+  int device = -1;
   cudaStream_t st = nullptr;
-  ~StreamGuard() { if (st) cudaStreamDestroy(st); }
+  double* p[9] = {nullptr};
+  size_t cap[9] = {0};
+  cudaError_t get(int k, size_t n, double** out) {
+    if (cap[k] < n) {
+      if (p[k]) cudaFree(p[k]);
+      p[k] = nullptr; cap[k] = 0;
+      cudaError_t e = cudaMalloc((void**)&p[k], std::max<size_t>(n, 1) * sizeof(double));
+      if (e != cudaSuccess) return e;
+      cap[k] = n;
+    }
+    *out = p[k];
+    return cudaSuccess;
+  }
+  void release() {
+    for (int k = 0; k < 9; ++k) { if (p[k]) cudaFree(p[k]); p[k] = nullptr; cap[k] = 0; }
+    if (st) cudaStreamDestroy(st);
+    st = nullptr;
+  }
 };
+Pool g_pool;
 
-struct Buf {
-  double* p = nullptr;
-  cudaError_t alloc(size_t n) { return cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(double)); }
-  ~Buf() { if (p) cudaFree(p); }
-};
+struct Buf { double* p = nullptr; };
+
+bool on_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return at.type == cudaMemoryTypeUnregistered || at.type == cudaMemoryTypeHost;
+}
 
 // (i p | j q) for i in occ1, p in virt1 (coefficients C1), j in occ2, q in virt2 (C2)
 int transform(cudaStream_t st, int N, const double* G, const double* C1, int no1, const double* C2, int no2,
@@ -187,43 +286,68 @@ int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, cons
   if (N <= 0 || na < 0 || nb < 0 || na > N || nb > N) return mp2_fail("pc_mp2_energy: bad sizes");
   if ((long long)N * N * N > 2147483647LL) return mp2_fail("pc_mp2_energy: N too large for this build");
   MP2_CUDA(cudaSetDevice(device));
-  StreamGuard guard;
-  MP2_CUDA(cudaStreamCreateWithFlags(&guard.st, cudaStreamNonBlocking));
-  cudaStream_t st = guard.st;
+  if (g_pool.device != device) { g_pool.release(); g_pool.device = device; }
+  if (!g_pool.st) MP2_CUDA(cudaStreamCreateWithFlags(&g_pool.st, cudaStreamNonBlocking));
+  cudaStream_t st = g_pool.st;
   const size_t NN = (size_t)N * N;
+  // restricted orbitals (RHF: the same coefficient and energy arrays for both spins): one
+  // transform serves all three sums
+  const bool restricted = na == nb && ((Ca == Cb && Ea == Eb) ||
+                                       (on_host(Ca) && on_host(Cb) && on_host(Ea) && on_host(Eb) &&
+                                        memcmp(Ca, Cb, NN * sizeof(double)) == 0 && memcmp(Ea, Eb, N * sizeof(double)) == 0));
   Buf dCa, dCb, dEa, dEb, T1, T2, T3, T4, out;
-  MP2_CUDA(dCa.alloc(NN)); MP2_CUDA(dCb.alloc(NN)); MP2_CUDA(dEa.alloc(N)); MP2_CUDA(dEb.alloc(N));
-  MP2_CUDA(out.alloc(3));
+  MP2_CUDA(g_pool.get(0, NN, &dCa.p)); MP2_CUDA(g_pool.get(1, NN, &dCb.p));
+  MP2_CUDA(g_pool.get(2, N, &dEa.p)); MP2_CUDA(g_pool.get(3, N, &dEb.p));
+  MP2_CUDA(g_pool.get(4, 3, &out.p));
   MP2_CUDA(cudaMemcpyAsync(dCa.p, Ca, NN * sizeof(double), cudaMemcpyDefault, st));
   MP2_CUDA(cudaMemcpyAsync(dCb.p, Cb, NN * sizeof(double), cudaMemcpyDefault, st));
   MP2_CUDA(cudaMemcpyAsync(dEa.p, Ea, N * sizeof(double), cudaMemcpyDefault, st));
   MP2_CUDA(cudaMemcpyAsync(dEb.p, Eb, N * sizeof(double), cudaMemcpyDefault, st));
   MP2_CUDA(cudaMemsetAsync(out.p, 0, 3 * sizeof(double), st));
   const int nom = std::max(na, nb), nvm = N - std::min(na, nb);
-  MP2_CUDA(T1.alloc((size_t)nom * NN * N));
-  MP2_CUDA(T2.alloc((size_t)nom * nvm * NN));
-  MP2_CUDA(T3.alloc((size_t)nom * nvm * nom * N));
-  MP2_CUDA(T4.alloc((size_t)nom * nvm * nom * nvm));
+  MP2_CUDA(g_pool.get(5, (size_t)nom * NN * N, &T1.p));
+  MP2_CUDA(g_pool.get(6, (size_t)nom * nvm * NN, &T2.p));
+  MP2_CUDA(g_pool.get(7, (size_t)nom * nvm * nom * N, &T3.p));
+  MP2_CUDA(g_pool.get(8, (size_t)nom * nvm * nom * nvm, &T4.p));
   const int blocks = 148 * 8;
-  if (same_spin && na > 0 && N - na > 0) {
-    if (transform(st, N, G_dev, dCa.p, na, dCa.p, na, T1, T2, T3, T4.p)) return 1;
-    mp2_same_spin_kernel<<<blocks, 256, 0, st>>>(na, N - na, T4.p, dEa.p, out.p);
-    MP2_CUDA(cudaGetLastError());
-  }
-  if (same_spin && nb > 0 && N - nb > 0) {
-    if (transform(st, N, G_dev, dCb.p, nb, dCb.p, nb, T1, T2, T3, T4.p)) return 1;
-    mp2_same_spin_kernel<<<blocks, 256, 0, st>>>(nb, N - nb, T4.p, dEb.p, out.p + 2);
-    MP2_CUDA(cudaGetLastError());
-  }
-  if (na > 0 && nb > 0 && N - na > 0 && N - nb > 0) {
-    if (transform(st, N, G_dev, dCa.p, na, dCb.p, nb, T1, T2, T3, T4.p)) return 1;
-    mp2_opp_spin_kernel<<<blocks, 256, 0, st>>>(na, N - na, nb, N - nb, T4.p, dEa.p, dEb.p, out.p + 1);
-    MP2_CUDA(cudaGetLastError());
+  if (restricted) {
+    if (na > 0 && N - na > 0) {
+      if (transform(st, N, G_dev, dCa.p, na, dCa.p, na, T1, T2, T3, T4.p)) return 1;
+      if (same_spin) {
+        mp2_same_spin_kernel<<<blocks, 256, 0, st>>>(na, N - na, T4.p, dEa.p, out.p);
+        MP2_CUDA(cudaGetLastError());
+      }
+      mp2_opp_spin_kernel<<<blocks, 256, 0, st>>>(na, N - na, na, N - na, T4.p, dEa.p, dEa.p, out.p + 1);
+      MP2_CUDA(cudaGetLastError());
+    }
+  } else {
+    if (same_spin && na > 0 && N - na > 0) {
+      if (transform(st, N, G_dev, dCa.p, na, dCa.p, na, T1, T2, T3, T4.p)) return 1;
+      mp2_same_spin_kernel<<<blocks, 256, 0, st>>>(na, N - na, T4.p, dEa.p, out.p);
+      MP2_CUDA(cudaGetLastError());
+    }
+    if (same_spin && nb > 0 && N - nb > 0) {
+      if (transform(st, N, G_dev, dCb.p, nb, dCb.p, nb, T1, T2, T3, T4.p)) return 1;
+      mp2_same_spin_kernel<<<blocks, 256, 0, st>>>(nb, N - nb, T4.p, dEb.p, out.p + 2);
+      MP2_CUDA(cudaGetLastError());
+    }
+    if (na > 0 && nb > 0 && N - na > 0 && N - nb > 0) {
+      if (transform(st, N, G_dev, dCa.p, na, dCb.p, nb, T1, T2, T3, T4.p)) return 1;
+      mp2_opp_spin_kernel<<<blocks, 256, 0, st>>>(na, N - na, nb, N - nb, T4.p, dEa.p, dEb.p, out.p + 1);
+      MP2_CUDA(cudaGetLastError());
+    }
   }
   double res[3];
   MP2_CUDA(cudaMemcpyAsync(res, out.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   MP2_CUDA(cudaStreamSynchronize(st));
-  *Eaa = res[0]; *Eab = res[1]; *Ebb = res[2];
+  *Eaa = res[0]; *Eab = res[1]; *Ebb = restricted ? res[0] : res[2];
+  return 0;
+}
+
+// frees the transform scratch kept between pc_mp2_energy calls
+int pc_mp2_release(void) {
+  g_pool.release();
+  g_pool.device = -1;
   return 0;
 }
 

@@ -240,11 +240,17 @@ class DeviceBasis:
             raise _lib.PychemB200Error("jk_direct: J/K digestion is defined for the repulsion integrals; "
                                        "call set_ints_type(0) (evaluate_2e_ints(molecule)) first")
         self._ensure_plan()
-        if variant is None and self.counts["nranks"] == 1:
-            variant = AUTO                          # classified on the device inside pc_jk_direct
         J, Xa, Xb = self._outputs(Dt)
         self._order_after_torch(Dt, Da, Db, J, Xa, Xb)
         if self.counts["nranks"] == 1:
+            if variant is None:
+                # classified on the device; closed-shell densities: X_beta is X_alpha (the same
+                # array object is returned for both, one device->host copy less; the reference's
+                # callers only read the exchange matrices, hartree_fock.py:354-355, noci.py:250-292)
+                v = ctypes.c_int()
+                _lib.check(self.lib.pc_jk_direct_auto(self.h, _ptr(Dt), _ptr(Da), _ptr(Db),
+                                                      _ptr(J), _ptr(Xa), _ptr(Xb), ctypes.byref(v)))
+                return (J, Xa, Xa) if v.value == RHF else (J, Xa, Xb)
             _lib.check(self.lib.pc_jk_direct(self.h, variant, _ptr(Dt), _ptr(Da), _ptr(Db),
                                              _ptr(J), _ptr(Xa), _ptr(Xb)))
             return J, Xa, Xb
@@ -262,10 +268,15 @@ class DeviceBasis:
         ev = torch.cuda.Event()
         ev.record(self.torch_stream())
         torch.cuda.current_stream().wait_event(ev)
-        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+        nn = self.nbf * self.nbf
+        # closed-shell: only [J | K_alpha] carry data (two thirds of the all-reduce, no X_beta copy)
+        dist.all_reduce(acc[:2 * nn] if variant == RHF else acc, op=dist.ReduceOp.SUM, group=group)
         ev2 = torch.cuda.Event()
         ev2.record(torch.cuda.current_stream())
         self.torch_stream().wait_event(ev2)
+        if variant == RHF:
+            _lib.check(self.lib.pc_jk_finalize(self.h, variant, _ptr(acc), _ptr(J), _ptr(Xa), None))
+            return J, Xa, Xa
         _lib.check(self.lib.pc_jk_finalize(self.h, variant, _ptr(acc), _ptr(J), _ptr(Xa), _ptr(Xb)))
         return J, Xa, Xb
 

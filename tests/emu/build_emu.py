@@ -47,6 +47,7 @@ const char* pc_mp2_last_error(void) { return "pc_mp2: not available in the host 
 int pc_mp2_energy(int, int, const double*, const double*, const double*, const double*, const double*, int, int,
                   int, double*, double*, double*) { return 1; }
 int pc_dgemm_dmma(int, int, int, int, const double*, const double*, double*) { return 1; }
+int pc_mp2_release(void) { return 0; }
 unsigned long long pcemu_launches(void) { return pcemu::ctx().launches; }
 unsigned long long pcemu_switches(void) { return pcemu::ctx().switches; }
 }

@@ -128,3 +128,59 @@ def test_benzene_mp2_transform_vs_numpy():
     assert abs(Ebb - Eaa) < 1e-12 * max(1.0, abs(Eaa))
     hf_gpu.release()
     ints_gpu.release()
+
+
+def test_benzene_mp2_sums_at_reference_orbitals(gold):
+    """BASELINE config 3, MP2 part: the reference's converged benzene/6-31G* orbitals and orbital
+    energies (tests/golden/benzene_631gs_rhf_mp2.npz, oracle/make_golden_benzene.py), integrals and
+    DMMA transform from the device, against the reference's formulas evaluated with numpy on the
+    reference's own tensor."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
+    g = gold("benzene_631gs_rhf_mp2.npz")
+    mol = helpers.molecule("benzene")
+    assert (mol.NAlphaElectrons, mol.NBetaElectrons) == (int(g["na"]), int(g["nb"]))
+    hf_gpu.evaluate_2e_ints(mol)
+    G = np.asarray(mol.CoulombIntegrals)
+    assert np.abs(G.ravel()[::9973] - g["G_sample"]).max() < 1e-12
+    assert abs(G.sum() - float(g["G_sum"])) < 1e-7
+    st = _state({"Ca": g["Ca"], "Cb": g["Cb"], "Ea": g["Ea"], "Eb": g["Eb"], "hf": g["energy_tight"]})
+    Eaa, Eab, Ebb = mp2_gpu.mp2_sums(mol, st)                 # restricted shortcut (Ca == Cb)
+    for mine, key in ((Eaa, "Eaa"), (Eab, "Eab"), (Ebb, "Ebb")):
+        assert abs(mine - float(g[key])) < 1e-10
+    assert abs(st.TotalEnergy + Eaa + Eab + Ebb - float(g["mp2_total"])) < E_TOL
+    # the general (three-transform) path on the same orbitals: beta perturbed in the last bits only
+    st.Beta.MOs = g["Cb"] * (1.0 + 1e-16)
+    st.Beta.MOs[0, 0] = np.nextafter(st.Beta.MOs[0, 0], 1.0)
+    Eaa2, Eab2, Ebb2 = mp2_gpu.mp2_sums(mol, st)
+    assert abs(Eaa2 - Eaa) < 1e-10 and abs(Eab2 - Eab) < 1e-10 and abs(Ebb2 - Ebb) < 1e-10
+    hf_gpu.release()
+    ints_gpu.release()
+
+
+@pytest.mark.skipif(not ref_driver.available(), reason="oracle/_ref (reference copy) not shipped")
+def test_benzene_rhf_mp2_dropin_through_reference_driver(gold, tmp_path):
+    """BASELINE config 3 end to end: pychem.main on benzene / 6-31G* / MP2 with the hot functions,
+    the one-electron matrices and mp2.do rebound to the CUDA path.  RHF total energy and the MP2
+    total the driver prints, within 1e-8 Eh of the reference (both SCF runs converged to
+    |dE| < 1e-11, see oracle/make_golden_hf_parts.py)."""
+    from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
+    from pychem_b200 import structures as S
+    g = gold("benzene_631gs_rhf_mp2.npz")
+    ns = ref_driver.modules()
+    undo1 = hf_gpu.install(ns.hartree_fock, one_electron=True)
+    undo2 = mp2_gpu.install(ns.mp2)
+    conv = ns.constants.energy_convergence
+    try:
+        inp = str(tmp_path / "benzene.inp")
+        ref_driver.write_input(inp, "benzene", S.benzene(), "6-31G*", method="MP2", maxiter=200)
+        ns.constants.energy_convergence = float(g["tight_convergence"])
+        mol = ref_driver.run(inp)
+    finally:
+        ns.constants.energy_convergence = conv
+        undo1()
+        undo2()
+    assert abs(mol.States[0].TotalEnergy - float(g["energy_tight"])) < E_TOL
+    emp2 = [float(l.split()[-1]) for l in mol.OutText.splitlines() if "Total MP2 energy" in l][0]
+    assert abs(emp2 - float(g["mp2_total"])) < E_TOL
+    hf_gpu.release()
+    ints_gpu.release()

@@ -213,3 +213,15 @@ def test_sampled_jk_oracle_matches_full_tensor_oracle():
     assert np.abs(J - J0)[mJ].max() < 1e-12
     assert np.abs(Xa - Xa0)[mX].max() < 1e-12
     assert np.abs(Xb - Xb0)[mX].max() < 1e-12
+
+
+def test_numpy_mp2_of_the_benzene_golden_matches_reference_mp2_on_h2o(gold):
+    """oracle/make_golden_benzene.py evaluates the reference's MP2 formulas (Methods/mp2.py:43-94)
+    with numpy.einsum because the reference's own loops cannot finish N = 96.  Pin that evaluation
+    on H2O / 6-31G**, where the reference's mp2.do did run (tests/golden/h2o_631gss_mp2.npz)."""
+    from oracle import oracle
+    from oracle.make_golden_benzene import mp2_numpy
+    g = gold("h2o_631gss_mp2.npz")
+    G = gold("h2o_631gss.npz")["G"]
+    Eaa, Eab, Ebb = mp2_numpy(G, g["Ca"], g["Cb"], g["Ea"], g["Eb"], int(g["na"]), int(g["nb"]))
+    assert abs(float(g["hf"]) + Eaa + Eab + Ebb - float(g["mp2_total"])) < 1e-10
