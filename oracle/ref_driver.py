@@ -91,14 +91,20 @@ def build_molecule(coords, basis, **kw):
         return molecule_from_input(path)
 
 
-def run(input_file, quiet=True):
-    """pychem.main(input_file) in a scratch directory (it writes <section>.out into cwd)."""
+def run(input_file, quiet=True, files=None):
+    """pychem.main(input_file) in a scratch directory (it writes <section>.out into cwd).
+    `files`: {name: 2-D array} written there first with numpy.savetxt -- the MO files of an
+    SCF_Guess = "READ" job (<MO_Read_Basis>_<state>.alpha_MOs / .beta_MOs, hartree_fock.py:35-41)."""
     ns = modules()
     input_file = os.path.abspath(input_file)
     cwd = os.getcwd()
     td = tempfile.mkdtemp()
     os.chdir(td)
     try:
+        if files:
+            import numpy
+            for name, arr in files.items():
+                numpy.savetxt(os.path.join(td, name), arr, fmt="%.17e")
         if quiet:
             with contextlib.redirect_stdout(io.StringIO()):
                 molecule = ns.pychem.main(input_file)

@@ -161,8 +161,14 @@ def test_benzene_mp2_sums_at_reference_orbitals(gold):
 def test_benzene_rhf_mp2_dropin_through_reference_driver(gold, tmp_path):
     """BASELINE config 3 end to end: pychem.main on benzene / 6-31G* / MP2 with the hot functions,
     the one-electron matrices and mp2.do rebound to the CUDA path.  RHF total energy and the MP2
-    total the driver prints, within 1e-8 Eh of the reference (both SCF runs converged to
-    |dE| < 1e-11, see oracle/make_golden_hf_parts.py)."""
+    total the driver prints, within 1e-8 Eh of the reference.
+
+    The SCF starts from the reference's converged orbitals (SCF_Guess = "READ", the driver's own
+    option, hartree_fock.py:35-41): benzene's core guess puts a degenerate pair at the Fermi level,
+    which of the two gets occupied is decided by rounding noise, and the reference's erratic DIIS
+    then lands on different stationary points (-253.0426 with its own integrals, -253.1089 here
+    from the core guess, integrals equal to 1e-14).  From the reference's orbitals the device
+    integrals must keep the SCF where it is: same stationary point, same energy, then MP2."""
     from pychem_b200 import hartree_fock as hf_gpu, integrals as ints_gpu, mp2 as mp2_gpu
     from pychem_b200 import structures as S
     g = gold("benzene_631gs_rhf_mp2.npz")
@@ -172,9 +178,10 @@ def test_benzene_rhf_mp2_dropin_through_reference_driver(gold, tmp_path):
     conv = ns.constants.energy_convergence
     try:
         inp = str(tmp_path / "benzene.inp")
-        ref_driver.write_input(inp, "benzene", S.benzene(), "6-31G*", method="MP2", maxiter=200)
+        ref_driver.write_input(inp, "benzene", S.benzene(), "6-31G*", method="MP2", maxiter=200,
+                               extra='SCF_Guess = "READ"\nMO_Read_Basis = "6-31G*"\nMO_Read_State = [0]')
         ns.constants.energy_convergence = float(g["tight_convergence"])
-        mol = ref_driver.run(inp)
+        mol = ref_driver.run(inp, files={"631GS_0.alpha_MOs": g["Ca"], "631GS_0.beta_MOs": g["Cb"]})
     finally:
         ns.constants.energy_convergence = conv
         undo1()
