@@ -461,6 +461,9 @@ class ClassGen:
         s.append("  if (JK) { fa0 = __ldg(I.bra.fx + i0); fc = __ldg(I.ket.fx + j); fd = __ldg(I.ket.fy + j); }")
         s.append("  const int kpid = JK ? __ldg(I.ket.pid + j) : 0;")
         s.append("  const int rmax = __reduce_max_sync(0xffffffffu, rseg);")
+        s.append("  // the records of the run's bra pairs are consecutive: pull their first lines into L1 now, every")
+        s.append("  // iteration of the run otherwise starts with an exposed L2 round trip for its header")
+        s.append("  for (int r = 1; r < rseg; ++r) pc_prefetch_l1(reinterpret_cast<const double2*>(I.bra.rec) + (size_t)min(i0 + r, nb - 1) * (3 * (I.bra.K + 1)));")
         s.append("  PcRunAcc<JKP ? MODE : PC_MODE_JK_RHF, %s> RA;" % dims)
         s.append("  if (JKP) pc_run_init(A, RA, fa0, fc, fd);")
         s.append("#pragma unroll 1")

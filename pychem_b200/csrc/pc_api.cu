@@ -128,6 +128,7 @@ struct PlanItem {
   const long long* seg_off;
   const int* seg_ij;       // int2 per segment
   const int* warp_s0;
+  const int* seg_rec;      // int4 per segment (+ sentinel): {off lo, off hi, ij.x, ij.y}
 };
 
 // the bucket pairs of one angular-momentum class that go into one fused kernel launch
@@ -200,7 +201,7 @@ struct pc_basis {
   // segment tables of ALL plan items, one allocation and one upload each (hundreds of bucket
   // pairs: per-item buffers cost more in cudaMalloc than the plan costs to build)
   DevBuf<long long> plan_seg_off;
-  DevBuf<int> plan_seg_ij, plan_warp_s0;
+  DevBuf<int> plan_seg_ij, plan_warp_s0, plan_seg_rec;
   long long my_quartets = 0, my_eris = 0, all_quartets = 0, all_eris = 0;
   // scratch
   DevBuf<double> acc, dstage, ostage;
@@ -503,6 +504,7 @@ int launch_group(pc_basis* h, int mode, const LaunchGroup& g, PcEriArgs& A, cuda
     PcItem& I = A.items[n++];
     fill_item(I, h->kinds[it.kb], h->kinds[it.kk]);
     I.seg_off = it.seg_off; I.seg_ij = (const int2*)it.seg_ij; I.warp_s0 = it.warp_s0;
+    I.seg_rec = (const int4*)it.seg_rec;
     I.nseg = it.nseg; I.t_begin = it.begin; I.t_count = it.count;
     I.same = it.same;
     I.warp0 = warp;
@@ -914,7 +916,7 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       it.total_q = w.seg_q.back(); it.count_q = it.total_q;
       it.prim_exec = w.seg_prim.back();
       it.nseg = (int)w.ij.size() / 2;
-      it.seg_off = nullptr; it.seg_ij = nullptr; it.warp_s0 = nullptr;
+      it.seg_off = nullptr; it.seg_ij = nullptr; it.warp_s0 = nullptr; it.seg_rec = nullptr;
       h->plan.push_back(it);
       widx.push_back((int)k);
     }
@@ -977,8 +979,10 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
       PC_CUDA(h->plan_seg_off.alloc(n_off));
       PC_CUDA(h->plan_seg_ij.alloc(n_ij));
       PC_CUDA(h->plan_warp_s0.alloc(n_s0));
+      PC_CUDA(h->plan_seg_rec.alloc(4 * n_off));
     }
     size_t o_off = 0, o_ij = 0, o_s0 = 0;       // w.ij holds int2 records: every item starts 8-byte aligned
+    std::vector<std::vector<int>> recs(h->plan.size());      // alive until the stream is synchronised below
     for (size_t k = 0; k < h->plan.size(); ++k) {
       PlanItem& it = h->plan[k];
       const Work& w = work[widx[k]];
@@ -991,6 +995,18 @@ int pc_plan(pc_basis* h, double thresh, int rank, int nranks, long long* my_quar
         PC_CUDA(cudaMemcpyAsync(h->plan_seg_off.p + o_off, w.seg_off.data(), w.seg_off.size() * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
         PC_CUDA(cudaMemcpyAsync(h->plan_seg_ij.p + o_ij, w.ij.data(), w.ij.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         PC_CUDA(cudaMemcpyAsync(h->plan_warp_s0.p + o_s0, w.s0.data(), w.s0.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        // merged decode records (one per seg_off entry, the sentinel included)
+        std::vector<int>& rec = recs[k];
+        rec.resize(4 * w.seg_off.size());
+        for (size_t sg = 0; sg < w.seg_off.size(); ++sg) {
+          const unsigned long long off = (unsigned long long)w.seg_off[sg];
+          rec[4 * sg] = (int)(unsigned)(off & 0xffffffffu);
+          rec[4 * sg + 1] = (int)(unsigned)(off >> 32);
+          rec[4 * sg + 2] = sg < (size_t)it.nseg ? w.ij[2 * sg] : 0;
+          rec[4 * sg + 3] = sg < (size_t)it.nseg ? w.ij[2 * sg + 1] : 0;
+        }
+        it.seg_rec = h->plan_seg_rec.p + 4 * o_off;
+        PC_CUDA(cudaMemcpyAsync(h->plan_seg_rec.p + 4 * o_off, rec.data(), rec.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         o_off += w.seg_off.size(); o_ij += w.ij.size(); o_s0 += w.s0.size();
       }
       const long long nsph = (long long)h->nfun(B->lx) * h->nfun(B->ly) * h->nfun(Kt->lx) * h->nfun(Kt->ly);

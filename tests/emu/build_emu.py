@@ -119,7 +119,7 @@ def build(jobs=None, regenerate=True):
             gen_eri.main(GEN)
     csrc_out = os.path.join(SRC, "pychem_b200", "csrc")
     headers = ["pc_common.cuh", "pc_one_electron.cuh", "pc_generic.cuh", "pc_generic_class.h", "pc_jk_kernels.cuh",
-               "pc_async.cuh"]
+               "pc_async.cuh", "pc_boys_table.h"]
     dep = hashlib.sha1()
     for hname in headers:
         t = transform(open(os.path.join(CSRC, hname)).read(), hname)
