@@ -404,7 +404,7 @@ class ClassGen:
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
         s.append("  switch (mode) {")
         for mode in MODES:
-            s.append("    case %s: eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode))
+            s.append("    case %s: pc_prefer_l1(eri_%s_kernel<%s>); eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode, self.name, mode))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")
         s.append("  return cudaGetLastError();")
@@ -415,7 +415,7 @@ class ClassGen:
         override = os.environ.get("PC_GEN_RUN_MINB_L%d" % self.L)
         if override:
             return int(override)
-        return {0: 8, 1: 6, 2: 5, 3: 4}.get(self.L, 3)
+        return {0: 8, 1: 6, 2: 4, 3: 4}.get(self.L, 3)     # L = 2: 4 beats 5 since the bra records (profiles/r2d_*)
 
     def source_run(self):
         """Run form: one thread = one ket pair x a run of bra pairs sharing their primary shell

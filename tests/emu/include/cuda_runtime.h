@@ -337,7 +337,7 @@ inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = null
 inline cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
 // every non-null pointer counts as device memory: host buffers are used in place
 inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void* p) { a->type = p ? cudaMemoryTypeDevice : cudaMemoryTypeUnregistered; a->device = 0; a->devicePointer = (void*)p; a->hostPointer = (void*)p; return cudaSuccess; }
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(1); return cudaSuccess; }
 inline cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = std::malloc(1); return cudaSuccess; }
