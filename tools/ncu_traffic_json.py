@@ -16,7 +16,7 @@ for f in files:
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
     for r in rows[2:]:
-        m = re.search(r"(eri_\w+_kernel)<\(int\)(\d)>", r[ix["Kernel Name"]]) or re.search(r"(jk_\w+_kernel)", r[ix["Kernel Name"]])
+        m = re.search(r"(eri_\w+_kernel)<(?:\(int\))?(\d)>", r[ix["Kernel Name"]]) or re.search(r"(jk_\w+_kernel)", r[ix["Kernel Name"]])
         if not m:
             continue
         name = m.group(1) + ("<%s>" % MODES.get(m.group(2), m.group(2)) if m.lastindex and m.lastindex > 1 else "")
