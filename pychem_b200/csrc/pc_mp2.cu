@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <mutex>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -248,6 +249,7 @@ struct Pool {
   }
 };
 Pool g_pool;
+std::mutex g_pool_mu;        // pc_mp2_energy / pc_mp2_release may be called from several host threads
 
 struct Buf { double* p = nullptr; };
 
@@ -285,6 +287,7 @@ int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, cons
   if (!G_dev || !Ca || !Cb || !Ea || !Eb || !Eaa || !Eab || !Ebb) return mp2_fail("pc_mp2_energy: null");
   if (N <= 0 || na < 0 || nb < 0 || na > N || nb > N) return mp2_fail("pc_mp2_energy: bad sizes");
   if ((long long)N * N * N > 2147483647LL) return mp2_fail("pc_mp2_energy: N too large for this build");
+  std::lock_guard<std::mutex> lock(g_pool_mu);
   MP2_CUDA(cudaSetDevice(device));
   if (g_pool.device != device) { g_pool.release(); g_pool.device = device; }
   if (!g_pool.st) MP2_CUDA(cudaStreamCreateWithFlags(&g_pool.st, cudaStreamNonBlocking));
@@ -346,6 +349,7 @@ int pc_mp2_energy(int device, int N, const double* G_dev, const double* Ca, cons
 
 // frees the transform scratch kept between pc_mp2_energy calls
 int pc_mp2_release(void) {
+  std::lock_guard<std::mutex> lock(g_pool_mu);
   g_pool.release();
   g_pool.device = -1;
   return 0;

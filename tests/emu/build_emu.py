@@ -76,6 +76,9 @@ def transform(text, name):
         return "pcemu::launch((unsigned)(%s), (unsigned)(%s), [&] { %s(%s); });" % (cfg[0], cfg[1], kern, args)
     # real-PTX regions that have a functional model under PC_HOST_EMU (pc_async.cuh)
     text = re.sub(r"// PC_EMU_SKIP_BEGIN.*?// PC_EMU_SKIP_END", "", text, flags=re.S)
+    text = text.replace('asm volatile("prefetch.global.L1 [%0];" ::"l"(row));', "(void)row;")
+    text = text.replace('asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));', "(void)row;")
+    text = text.replace("__frcp_rn((float)sPQ)", "(1.0f / (float)sPQ)")
     text, n = LAUNCH.subn(repl, text)
     if name == "pc_common.cuh":
         if RSQRT_ASM not in text or PREFETCH_ASM not in text or LDG256_ASM not in text:
