@@ -412,11 +412,20 @@ class ClassGen:
         s = []
         s.append("cudaError_t pc_launch_%s(int mode, const PcEriArgs& A, cudaStream_t st) {" % self.name)
         s.append("  if (A.nwarps <= 0) return cudaSuccess;")
+        if getattr(self, "coop", None) is not None:
+            s.extend(self.coop.launch_lines())
         s.append("  const int block = %d;" % block)
         s.append("  const unsigned grid = (unsigned)(((long long)A.nwarps * 32 + block - 1) / block);")
+        # experiment: cap the resident CTAs per SM with unused dynamic shared memory (keeps the
+        # local-memory footprint of the spilling classes inside L1)
+        cap = int(os.environ.get("PC_GEN_OCC_CAP_L%d" % self.L, "0"))
+        dyn = (200 * 1024 // cap) if cap else 0
         s.append("  switch (mode) {")
         for mode in MODES:
-            s.append("    case %s: pc_prefer_l1(eri_%s_kernel<%s>); eri_%s_kernel<%s><<<grid, block, 0, st>>>(A); break;" % (mode, self.name, mode, self.name, mode))
+            pre = "pc_prefer_l1(eri_%s_kernel<%s>);" % (self.name, mode)
+            if cap:
+                pre = "cudaFuncSetAttribute(eri_%s_kernel<%s>, cudaFuncAttributeMaxDynamicSharedMemorySize, %d);" % (self.name, mode, dyn)
+            s.append("    case %s: %s eri_%s_kernel<%s><<<grid, block, %d, st>>>(A); break;" % (mode, pre, self.name, mode, dyn))
         s.append("    default: return cudaErrorInvalidValue;")
         s.append("  }")
         s.append("  return cudaGetLastError();")
@@ -544,6 +553,8 @@ class ClassGen:
                  % (LNAME[lx1], LNAME[ly1], LNAME[lx2], LNAME[ly2], " [rolled form]" if self.V2 else "",
                     self.L, self.ne, self.nf, self.n_vrr, self.n_tail))
         s.append('#include "../pc_common.cuh"')
+        if self.name in COOP_CLASSES and not self.cart_d:
+            s.append('#include "../pc_async.cuh"')
         s.append("")
         s.append("namespace {")
         s.append("constexpr int L = %d, NE = %d, NF = %d, NSPH = %d;" % (self.L, self.ne, self.nf, nsp))
@@ -582,6 +593,10 @@ class ClassGen:
             s.append("  " + line)
         s.append("  pc_epilogue<MODE, %s>(A, I, t, valid, fa, fb, pidb, j, seg_lo, seg_hi, g, S);" % dims)
         s.append("}")
+        self.coop = None
+        if self.name in COOP_CLASSES and not self.cart_d:
+            self.coop = CoopGen(self, COOP_CLASSES[self.name])
+            s.extend(self.coop.source())
         s.append("}  // namespace")
         s.append("")
         s.extend(self.launcher(block))
@@ -844,6 +859,277 @@ class ClassGenV2(ClassGen):
         self.c2s_ops = ops1 + em.ops * nqs
         self.n_tail = n1 + em.n
         return lines
+
+
+class CoopGen:
+    """Warp-cooperative form of a high-L class: the CTA is G warps that hold the SAME 32 quartets
+    (lane = quartet, warp = role).  One thread per quartet keeps ne x nf contracted (e0|f0) and a
+    few hundred recursion temporaries alive -- (dp|pp) spills 1.8 KB per thread, and ncu shows the
+    spill lines travelling to L2 and DRAM (1.1 GB written per launch).  Here
+      phase 1  role r runs the primitive loops for ITS bra components e (the chains of the bra
+               recursion that end in its d/p/s ancestors: the bra build lowers one fixed direction
+               per component, so the chains only share the low end), keeps ne_r x nf accumulators in
+               registers, and finishes with the ket HRR + cart->spherical of its rows; the
+               (e0|cd) rows go to shared memory [e][q][lane];
+      phase 2  role r takes the ket functions c of ITS range: bra HRR + cart->spherical from shared
+               memory, then the J/K digestion of the (a b | c_r d) sub-block.
+    The redundant work is the shared low end of the recursion (x1.2-1.4 arithmetic in total); no
+    accumulator leaves the registers.  Instantiated for the single-set J/K modes and NULL; the other
+    modes (tensor / block output, scattering, batched density sets) stay on the one-thread kernel."""
+
+    MODES = ("PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL")
+
+    def __init__(self, base, G):
+        self.b = base
+        lx1, ly1, lx2, ly2 = base.l
+        NA, NB, NC, ND = base.nsph
+        split = os.environ.get("PC_GEN_COOP_SPLIT", "d")          # phase 2 by ket function d (default) or c
+        if ND == 1:
+            split = "c"
+        self.G = G = min(G, ND if split == "d" else NC, ncart(lx1))
+        self.nq = NC * ND
+
+        def anc(e):
+            while sum(e) > lx1:
+                e = dec(e, first_dir(e))
+            return e
+        chains = {}
+        for e in base.e_list:
+            chains.setdefault(anc(e), []).append(e)
+
+        def cost(es):
+            return sum(l.count("fma(") + l.count(" * ") for l in self.sub(es).gen_vrr())
+        bins = [[] for _ in range(G)]
+        for _, es in sorted(chains.items(), key=lambda kv: -cost(kv[1])):
+            best = min(range(G), key=lambda r: (cost(bins[r] + es), r))
+            bins[best] = bins[best] + es
+        order = {e: k for k, e in enumerate(base.e_list)}
+        self.egroups = [sorted(b, key=order.get) for b in bins]
+        # phase 2: role r digests the sub-block (a b | c0..c0+ncs-1, d0..d0+nds-1).  Split by d where
+        # the ket's second shell has functions to split: the per-lane images J[c,d], K[a,d], K[b,d]
+        # then belong to one role each (a split by c would repeat K[a,d] and K[b,d] in every role)
+        self.sub_blocks = []
+        tot = ND if split == "d" else NC
+        x0 = 0
+        for r in range(G):
+            n = tot // G + (1 if r < tot % G else 0)
+            self.sub_blocks.append((0, NC, x0, n) if split == "d" else (x0, n, 0, ND))
+            x0 += n
+        # with whole ket shells c in every role the segment-shared images J[a,b], K[a,c], K[b,c] of the
+        # roles are partial sums of the same elements: left in shared memory and reduced by the CTA
+        self.defer = split == "d" and os.environ.get("PC_GEN_COOP_DEFER", "1") != "0"
+        self.max_acc = max(len(es) for es in self.egroups) * base.nf
+
+    def sub(self, es):
+        g = ClassGen(*self.b.l)
+        g.e_list = list(es)
+        g.ne = len(es)
+        return g
+
+    def ket_tail(self, r):
+        """ket HRR + cart->spherical of role r's (e0| rows; results to shared memory."""
+        b = self.b
+        lx1, ly1, lx2, ly2 = b.l
+        em = Emit("hk")
+        f_index = {c: i for i, c in enumerate(b.f_list)}
+        e_glob = {c: i for i, c in enumerate(b.e_list)}
+        out = []
+        for il, e in enumerate(self.egroups[r]):
+            memo = {}
+
+            def hk(cx, cy):
+                key = (cx, cy)
+                if key in memo:
+                    return memo[key]
+                if sum(cy) == 0:
+                    val = "acc[%d]" % (il * b.nf + f_index[cx])
+                else:
+                    d = first_dir(cy)
+                    cy0 = dec(cy, d)
+                    val = em.new("fma(CD%d, %s, %s)" % (d, hk(cx, cy0), hk(inc(cx, d), cy0)))
+                memo[key] = val
+                return val
+
+            cart = {(ix, iy): hk(cx, cy) for ix, cx in enumerate(comps(lx2)) for iy, cy in enumerate(comps(ly2))}
+            half = {}
+            for ix in range(ncart(lx2)):
+                for my, row in enumerate(c2s_rows(ly2)):
+                    half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
+            for mx, row in enumerate(c2s_rows(lx2)):
+                for my in range(nsph(ly2)):
+                    v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
+                    q = mx * nsph(ly2) + my
+                    out.append("ks_sm[%d + lane] = %s;" % ((e_glob[e] * self.nq + q) * 32, v))
+        return em.lines + out
+
+    def bra_tail(self, r):
+        """bra HRR + cart->spherical for the ket functions c of role r: g[(a b)][c_local][d]."""
+        b = self.b
+        lx1, ly1, lx2, ly2 = b.l
+        NA, NB, NC, ND = b.nsph
+        c0, ncs, d0, nds = self.sub_blocks[r]
+        em = Emit("hb")
+        e_glob = {c: i for i, c in enumerate(b.e_list)}
+        out = []
+        nqs = ncs * nds
+        for cl in range(ncs):
+            for dl in range(nds):
+                q = (c0 + cl) * ND + d0 + dl
+                ql = cl * nds + dl
+                memo = {}
+
+                def hb(cx, cy):
+                    key = (cx, cy)
+                    if key in memo:
+                        return memo[key]
+                    if sum(cy) == 0:
+                        val = em.new("ks_sm[%d + lane]" % ((e_glob[cx] * self.nq + q) * 32))
+                    else:
+                        d = first_dir(cy)
+                        cy0 = dec(cy, d)
+                        val = em.new("fma(AB%d, %s, %s)" % (d, hb(cx, cy0), hb(inc(cx, d), cy0)))
+                    memo[key] = val
+                    return val
+
+                cart = {(ix, iy): hb(cx, cy) for ix, cx in enumerate(comps(lx1)) for iy, cy in enumerate(comps(ly1))}
+                half = {}
+                for ix in range(ncart(lx1)):
+                    for my, row in enumerate(c2s_rows(ly1)):
+                        half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
+                for mx, row in enumerate(c2s_rows(lx1)):
+                    for my in range(nsph(ly1)):
+                        v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
+                        pidx = mx * nsph(ly1) + my
+                        out.append("g[%d] = %s;" % (pidx * nqs + ql, v))
+        return em.lines + out
+
+    def min_blocks(self):
+        override = os.environ.get("PC_GEN_COOP_MINB")
+        if override:
+            return int(override)
+        return 2
+
+    def smem_bytes(self, mode):
+        NA, NB, NC, ND = self.b.nsph
+        n = self.b.ne * self.nq * 32
+        if self.defer and mode != "PC_MODE_NULL":
+            gen = mode == "PC_MODE_JK_GEN"
+            ks = NA * NC + NB * NC + (NC * NB + NC * NA if gen else 0)
+            n += self.G * (NA * NB + (1 if mode == "PC_MODE_JK_RHF" else 2) * ks) * 33
+        return n * 8
+
+    def source(self):
+        """kernel text (inside the class file's anonymous namespace)"""
+        b = self.b
+        G = self.G
+        NA, NB, NC, ND = b.nsph
+        nmax = max(b.La, b.Lc, 1)
+        big = max(self.sub_blocks, key=lambda sb: sb[1] * sb[3])
+        s = []
+        s.append("")
+        s.append("// ---- warp-cooperative form: %d roles; bra components per role %s; ket functions per role %s"
+                 % (G, [len(e) for e in self.egroups], ["%dx%d" % (sb[1], sb[3]) for sb in self.sub_blocks]))
+        s.append("template <int MODE>")
+        maxnreg = int(os.environ.get("PC_GEN_COOP_MAXNREG", "0"))
+        bounds = "PC_MAXNREG(%d)" % maxnreg if maxnreg else "__launch_bounds__(%d, %d)" % (32 * G, self.min_blocks())
+        s.append("__global__ void %s eri_%s_coop_kernel(const __grid_constant__ PcEriArgs A) {" % (bounds, b.name))
+        s.append("  typedef PcSegScratch<PcSegNeed<MODE, %d, %d, %d, %d, false>::ROWS> Scratch;" % (NA, NB, big[1], big[3]))
+        s.append("  __shared__ Scratch seg_scratch[%d];" % G)
+        s.append("  PC_DYN_SMEM(ks_raw);")
+        s.append("  double* __restrict__ ks_sm = reinterpret_cast<double*>(ks_raw);      // [e][q][lane]")
+        if self.defer:
+            s.append("  typedef PcCoopCount<MODE, %d, %d, %d, %d> Coop;" % (NA, NB, NC, G))
+            s.append("  double* __restrict__ part = ks_sm + %d;                          // [role][value][33]" % (b.ne * self.nq * 32))
+            s.append("  __shared__ PcCoopSeg coop_seg;")
+        s.append("  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;")
+        s.append("  Scratch* S = &seg_scratch[role];")
+        s.append("  const int gw = blockIdx.x;                                           // the CTA's 32 quartets")
+        s.append("  const PcItem& I = A.items[pc_find_item(A, gw)];")
+        s.append("  const long long t = (long long)(gw - I.warp0) * 32 + lane;")
+        s.append("  int i, j, seg_lo, seg_hi;")
+        s.append("  bool valid;")
+        s.append("  if (!pc_decode_live(A, I, t, i, j, seg_lo, seg_hi, valid)) return;   // same answer in every role")
+        b.bra_record(s, "i")
+        s.append("  const int fa = bh2.x;")
+        s.append("  const int nk = I.ket.n, KK = __ldg(I.ket.keff + j);")
+        if os.environ.get("PC_GEN_COOP_PREFETCH", "1") != "0":
+            s.append("  if (role == %d && MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)   // one role warms L1 for the CTA's digestion" % (G - 1))
+            s.append("    pc_prefetch_density<%d, %d, %d, %d>(A, fa, fb, __ldg(I.ket.fx + j), __ldg(I.ket.fy + j), MODE != PC_MODE_JK_GEN);" % (NA, NB, NC, ND))
+        s.append("  const double CD0 = __ldg(I.ket.xy + j), CD1 = __ldg(I.ket.xy + nk + j), CD2 = __ldg(I.ket.xy + 2 * nk + j);")
+        s.append("  {")
+        s.append("  double acc[%d];" % self.max_acc)
+        s.append("#pragma unroll")
+        s.append("  for (int k = 0; k < %d; ++k) acc[k] = 0.0;" % self.max_acc)
+        b.prim_prologue(s, nmax)
+        s.append("      switch (role) {")
+        for r in range(G):
+            s.append("      case %d: {" % r)
+            for line in self.sub(self.egroups[r]).gen_vrr():
+                s.append("        " + line)
+            s.append("      } break;")
+        s.append("      }")
+        b.close_prim_loops(s)
+        s.append("  (void)CD0; (void)CD1; (void)CD2;")
+        s.append("  switch (role) {")
+        for r in range(G):
+            s.append("  case %d: {" % r)
+            for line in self.ket_tail(r):
+                s.append("    " + line)
+            s.append("  } break;")
+        s.append("  }")
+        s.append("  }")
+        s.append("  __syncthreads();")
+        s.append("  (void)AB0; (void)AB1; (void)AB2;")
+        s.append("  switch (role) {")
+        for r in range(G):
+            c0, ncs, d0, nds = self.sub_blocks[r]
+            s.append("  case %d: {" % r)
+            s.append("    double g[%d];" % (NA * NB * ncs * nds))
+            for line in self.bra_tail(r):
+                s.append("    " + line)
+            if self.defer:
+                s.append("    pc_epilogue_sub<MODE, %d, %d, %d, %d>(A, I, valid, fa, fb, pidb, j, %d, %d, seg_lo, seg_hi, g, S, PcReduceDefer{part + %d * Coop::NVT * 33});"
+                         % (NA, NB, ncs, nds, c0, d0, r))
+            else:
+                s.append("    pc_epilogue_sub<MODE, %d, %d, %d, %d>(A, I, valid, fa, fb, pidb, j, %d, %d, seg_lo, seg_hi, g, S);"
+                         % (NA, NB, ncs, nds, c0, d0))
+            s.append("  } break;")
+        s.append("  }")
+        if self.defer:
+            s.append("  if (MODE != PC_MODE_NULL) {")
+            s.append("    const unsigned ends = __ballot_sync(0xffffffffu, valid && lane == seg_hi);")
+            s.append("    if (role == 0) coop_seg.idx[lane] = make_int4(fa, fb, __ldg(I.ket.fx + j), seg_lo);")
+            s.append("    __syncthreads();")
+            s.append("    pc_coop_reduce<MODE, %d, %d, %d, %d>(A, part, &coop_seg, ends);" % (NA, NB, NC, G))
+            s.append("  }")
+        s.append("}")
+        return s
+
+    def launch_lines(self):
+        b = self.b
+        s = []
+        s.append("  static const bool coop = []() { const char* e = getenv(\"PYCHEM_B200_COOP\"); return !(e && e[0] == '0'); }();")
+        s.append("  if (coop) {")
+        s.append("    switch (mode) {")
+        for mode in MODES:
+            if mode in self.MODES:
+                s.append("      case %s: {" % mode)
+                s.append("        static bool attr = false;")
+                s.append("        if (!attr) { attr = true; cudaFuncSetAttribute(eri_%s_coop_kernel<%s>, cudaFuncAttributeMaxDynamicSharedMemorySize, %d); }"
+                         % (b.name, mode, self.smem_bytes(mode)))
+                s.append("        eri_%s_coop_kernel<%s><<<(unsigned)A.nwarps, %d, %d, st>>>(A);" % (b.name, mode, 32 * self.G, self.smem_bytes(mode)))
+                s.append("        return cudaGetLastError();")
+                s.append("      }")
+        s.append("      default: break;")
+        s.append("    }")
+        s.append("  }")
+        return s
+
+
+# classes built in the warp-cooperative form as well, and their number of roles
+COOP_CLASSES = {}
+if os.environ.get("PC_GEN_COOP"):
+    COOP_CLASSES = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in os.environ["PC_GEN_COOP"].split(",") if kv and kv != "0")
 
 
 # bra-record prefetch: 0 = none (the record's lines hit L1 after the first touch), 1 = next primitive

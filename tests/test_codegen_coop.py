@@ -1,0 +1,60 @@
+"""Generator check of the warp-cooperative kernel form (PC_GEN_COOP, an opt-in experiment of
+pychem_b200/codegen/gen_eri.py, profiles/r2e_cooperative_high_l.txt): the roles must partition the
+bra components of the contracted (e0|f0) and the ket functions of the sub-blocks exactly once, and
+the generated text must carry one kernel + launcher branch per supported mode.  Numerics of the
+form are checked on the host emulation when a variant is built (tools/build_variant.py --emu)."""
+import importlib
+import os
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture()
+def gen(monkeypatch):
+    monkeypatch.setenv("PC_GEN_COOP", "dppp=3,dpdp=3,dpds=3")
+    sys.path.insert(0, os.path.join(HERE, "..", "pychem_b200", "codegen"))
+    import gen_eri
+    mod = importlib.reload(gen_eri)
+    yield mod
+    monkeypatch.delenv("PC_GEN_COOP")
+    importlib.reload(gen_eri)
+    sys.path.pop(0)
+
+
+@pytest.mark.parametrize("cls,split", [((2, 1, 1, 1), "d"), ((2, 1, 2, 1), "d"), ((2, 1, 2, 0), "c")])
+def test_roles_partition_components_and_sub_blocks(gen, cls, split):
+    base = gen.ClassGen(*cls)
+    coop = gen.CoopGen(base, 3)
+    assert coop.G == 3
+    flat = [e for grp in coop.egroups for e in grp]
+    assert sorted(flat) == sorted(base.e_list) and len(set(flat)) == len(flat)
+    NA, NB, NC, ND = base.nsph
+    seen = set()
+    for c0, ncs, d0, nds in coop.sub_blocks:
+        for c in range(c0, c0 + ncs):
+            for d in range(d0, d0 + nds):
+                assert (c, d) not in seen
+                seen.add((c, d))
+    assert len(seen) == NC * ND
+    assert coop.defer == (split == "d")
+    # every role's recursion is a pruned copy of the class's: no more temporaries than the whole
+    base.gen_vrr()
+    for grp in coop.egroups:
+        sub = coop.sub(grp)
+        sub.gen_vrr()
+        assert 0 < sub.n_vrr < base.n_vrr
+
+
+def test_generated_text(gen):
+    g = gen.make_class((2, 1, 1, 1))
+    src = g.source()
+    assert "eri_dppp_coop_kernel" in src and "pc_coop_reduce<MODE, 5, 3, 3, 3>" in src
+    for mode in gen.CoopGen.MODES:
+        assert "eri_dppp_coop_kernel<%s><<<" % mode in src
+    assert "eri_dppp_coop_kernel<PC_MODE_TENSOR>" not in src         # other modes stay on the one-thread kernel
+    assert "PYCHEM_B200_COOP" in src
+    plain = gen.make_class((1, 1, 1, 0)).source()                    # a class outside PC_GEN_COOP is untouched
+    assert "coop" not in plain
