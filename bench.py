@@ -429,19 +429,31 @@ def run_b200(args):
         for _ in range(max(args.warmup, 3)):
             hf_gpu.make_coulomb_exchange_matrices(main.mol, state)
         barrier()
+        prof = None
+        if os.environ.get("PYCHEM_B200_BENCH_PROFILE") and rank == 0:      # diagnostic: host profile of the e2e loop
+            import cProfile
+            prof = cProfile.Profile()
+            prof.enable()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             hf_gpu.make_coulomb_exchange_matrices(main.mol, state)
         barrier()
         t = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], dtype=torch.float64, device=dev)
+        if prof is not None:
+            import pstats
+            prof.disable()
+            pstats.Stats(prof, stream=sys.stderr).sort_stats("cumulative").print_stats(30)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), state
 
     e2e_ms, state = e2e_run(pinned=True)
-    e2e_page_ms, _ = e2e_run(pinned=False)
+    # (results of the N > 1 path are views of the shared host buffer, valid until the next call: compare now)
+    err = max(float(np.abs(state.Total.Coulomb - J_dev_host).max()), float(np.abs(state.Alpha.Exchange - Xa_dev_host).max()))
+    e2e_page_ms, state_p = e2e_run(pinned=False)
+    err = max(err, float(np.abs(state_p.Total.Coulomb - J_dev_host).max()))
     e2e_value = counts["all_eris"] / (e2e_ms * 1e-3)
-    err = float(np.abs(state.Total.Coulomb - J_dev_host).max())
+    shared = bool(getattr(db, "_share", None) and db._share[1] is not None)
 
     # ---- roofline: per-class device times (one profiled build), FP64 peak measured live ------
     db.set_profiling(True)
@@ -561,7 +573,15 @@ def run_b200(args):
                 "eri_generation_only": {"ms_per_pass": eri_only_ms, "value": counts["all_eris"] / (eri_only_ms * 1e-3), "unit": UNIT},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                        "h2d_bytes_per_step": 3 * N * N * 8, "d2h_bytes_per_step": 2 * N * N * 8,
+                        # bytes moved over PCIe by ALL ranks per step.  N > 1 on one node: every rank uploads
+                        # 1/N of the rows of each density (all-gather over NVLink) and downloads 1/N of the
+                        # rows of J and X into the host buffer the ranks share (pychem_b200/dist.py NodeShare)
+                        "h2d_bytes_per_step": 3 * N * N * 8 * (1 if shared or world == 1 else world),
+                        "d2h_bytes_per_step": 2 * N * N * 8 * (1 if shared or world == 1 else world),
+                        "h2d_bytes_per_step_per_rank": 3 * N * N * 8 // (world if shared else 1),
+                        "d2h_bytes_per_step_per_rank": 2 * N * N * 8 // (world if shared else 1),
+                        "host_traffic": ("row slices per rank, results in a host buffer shared by the ranks" if shared
+                                         else "whole matrices per rank"),
                         "call": "pychem_b200.hartree_fock.make_coulomb_exchange_matrices(molecule, state), three pinned host "
                                 "densities in, J / X host arrays out (closed-shell result: X_beta is the X_alpha array, 2 N^2 doubles back)",
                         "pageable_inputs": {"ms_per_step": e2e_page_ms, "value": counts["all_eris"] / (e2e_page_ms * 1e-3),

@@ -1263,10 +1263,20 @@ int pc_jk_direct_accumulate(pc_basis* h, int variant, const double* Dt, const do
     PC_CUDA(cudaEventRecord(h->ev_fork, h->stream));
     for (int s2 = 0; s2 < NSIDE; ++s2) PC_CUDA(cudaStreamWaitEvent(h->side[s2], h->ev_fork, 0));
   }
+  // measurement aid (tools/run_r2_floor.sh): PYCHEM_B200_DEBUG_LRANGE=lo,hi launches only the classes
+  // with lo <= L <= hi -- the result is then incomplete by construction, the timing shows which
+  // classes the concurrent step rests on
+  static const int LR[2] = {[]() { const char* e = getenv("PYCHEM_B200_DEBUG_LRANGE"); return e ? atoi(e) : 0; }(),
+                            []() { const char* e = getenv("PYCHEM_B200_DEBUG_LRANGE"); const char* c = e ? strchr(e, ',') : nullptr; return c ? atoi(c + 1) : 99; }()};
+  static const int pair_l[6] = {0, 1, 2, 2, 3, 4};       // ss ps pp ds dp dd
   size_t idx = 0;
   for (const LaunchGroup& g : h->groups) {
     if (h->profiling) PC_CUDA(cudaEventRecord(h->prof_events[idx], h->stream));
     ++idx;
+    if (g.pcb < 6 && g.pck < 6) {
+      const int Lg = pair_l[g.pcb] + pair_l[g.pck];
+      if (Lg < LR[0] || Lg > LR[1]) continue;
+    }
     PcEriArgs A;
     memset(&A, 0, sizeof(A));
     A.Dj = dt; A.Da = da; A.Db = db;

@@ -72,7 +72,16 @@ class DeviceBasis:
         self._acc = None
         self.ints_type = 0
 
+    def drop_share(self):
+        """Release the host buffer shared with the other ranks (the next multi-rank jk_direct with
+        host arrays sets it up again, reading PYCHEM_B200_SHARED_RESULTS)."""
+        cur = getattr(self, "_share", None)
+        if cur is not None and cur[1] is not None:
+            cur[1].close()
+        self._share = None
+
     def close(self):
+        self.drop_share()
         if getattr(self, "h", None):
             self.lib.pc_basis_destroy(self.h)
             self.h = None
@@ -234,14 +243,21 @@ class DeviceBasis:
 
     def jk_direct(self, Dt, Da, Db, variant=None, group=None):
         """Integral-direct J/K.  With an initialised torch.distributed process group and a plan
-        built with nranks>1, partial accumulators are summed with one NCCL all-reduce."""
+        built with nranks>1, partial accumulators are summed with one NCCL all-reduce.  With host
+        (numpy) densities and all ranks on one node, every rank moves only its share of the rows of
+        the densities and of the results over PCIe; the result arrays are then views of a buffer the
+        ranks share and stay valid until the next jk_direct call on this basis."""
         Dt, Da, Db = _as_f64(Dt), _as_f64(Da), _as_f64(Db)
         if self.ints_type != 0:
             raise _lib.PychemB200Error("jk_direct: J/K digestion is defined for the repulsion integrals; "
                                        "call set_ints_type(0) (evaluate_2e_ints(molecule)) first")
         self._ensure_plan()
-        J, Xa, Xb = self._outputs(Dt)
-        self._order_after_torch(Dt, Da, Db, J, Xa, Xb)
+        share = None
+        if self.counts["nranks"] > 1 and isinstance(Dt, np.ndarray):
+            share = self._node_share(group)
+        if share is None:
+            J, Xa, Xb = self._outputs(Dt)
+            self._order_after_torch(Dt, Da, Db, J, Xa, Xb)
         if self.counts["nranks"] == 1:
             if variant is None:
                 # classified on the device; closed-shell densities: X_beta is X_alpha (the same
@@ -257,6 +273,10 @@ class DeviceBasis:
         import torch
         import torch.distributed as dist
         acc = self.accumulator()
+        if share is not None:
+            # 1/nranks of the rows of every density over this rank's PCIe link, the rest over NVLink
+            Dt, Da, Db = self._gather_densities(share, Dt, Da, Db, group)
+            self._order_after_torch(Dt)
         if variant is None:
             v = ctypes.c_int()
             _lib.check(self.lib.pc_jk_direct_accumulate_auto(self.h, _ptr(Dt), _ptr(Da), _ptr(Db), _ptr(acc),
@@ -274,11 +294,74 @@ class DeviceBasis:
         ev2 = torch.cuda.Event()
         ev2.record(torch.cuda.current_stream())
         self.torch_stream().wait_event(ev2)
+        if share is not None:
+            return self._finalize_shared(share, variant, acc)
         if variant == RHF:
             _lib.check(self.lib.pc_jk_finalize(self.h, variant, _ptr(acc), _ptr(J), _ptr(Xa), None))
             return J, Xa, Xa
         _lib.check(self.lib.pc_jk_finalize(self.h, variant, _ptr(acc), _ptr(J), _ptr(Xa), _ptr(Xb)))
         return J, Xa, Xb
+
+    # ---- host traffic of the N>1 path, sharded over the ranks' PCIe links (pychem_b200/dist.py NodeShare)
+    def _node_share(self, group):
+        """NodeShare of this basis and group, or None (one node only; PYCHEM_B200_SHARED_RESULTS=0
+        switches it off: every rank then moves whole matrices over its own link)."""
+        import os
+        key = id(group)
+        cur = getattr(self, "_share", None)
+        if cur is not None and cur[0] == key:
+            return cur[1]
+        sh = None
+        if os.environ.get("PYCHEM_B200_SHARED_RESULTS", "1") != "0":
+            from . import dist as pdist
+            try:
+                sh = pdist.NodeShare((3, self.nbf, self.nbf), group=group)
+            except pdist.NodeShareUnavailable:
+                sh = None                              # (a collective decision: the same on every rank)
+        self._share = (key, sh)
+        return sh
+
+    def _gather_densities(self, share, Dt, Da, Db, group):
+        import torch
+        import torch.distributed as dist
+        N, W = self.nbf, share.world
+        R = (N + W - 1) // W
+        dev = "cuda:%d" % self.device
+        if getattr(self, "_dens_dev", None) is None:
+            self._dens_chunk = torch.zeros((3, R, N), dtype=torch.float64, device=dev)
+            self._dens_all = torch.empty((W, 3, R, N), dtype=torch.float64, device=dev)
+            self._dens_dev = torch.empty((3, W * R, N), dtype=torch.float64, device=dev)
+        lo, hi = share.rows(N)
+        same = Db is Da
+        for m, D in enumerate((Dt, Da, Db)):
+            if m == 2 and same:
+                break
+            if hi > lo:
+                self._dens_chunk[m, :hi - lo].copy_(torch.from_numpy(D[lo:hi]), non_blocking=True)
+        dist.all_gather_into_tensor(self._dens_all.view(-1), self._dens_chunk.view(-1), group=group)
+        self._dens_dev.view(3, W, R, N).copy_(self._dens_all.permute(1, 0, 2, 3))
+        full = self._dens_dev
+        return full[0, :N], full[1, :N], (full[1, :N] if same else full[2, :N])
+
+    def _finalize_shared(self, share, variant, acc):
+        import torch
+        N = self.nbf
+        dev = "cuda:%d" % self.device
+        if getattr(self, "_out_dev", None) is None:
+            self._out_dev = torch.empty((3, N, N), dtype=torch.float64, device=dev)
+        out = self._out_dev
+        nout = 2 if variant == RHF else 3
+        _lib.check(self.lib.pc_jk_finalize(self.h, variant, _ptr(acc), _ptr(out[0]), _ptr(out[1]),
+                                           None if variant == RHF else _ptr(out[2])))
+        buf = share.buffer()
+        lo, hi = share.rows(N)
+        if hi > lo:
+            host = torch.from_numpy(buf)
+            for m in range(nout):                      # contiguous row blocks: plain async copies
+                host[m, lo:hi].copy_(out[m, lo:hi], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        share.barrier()
+        return buf[0], buf[1], (buf[1] if variant == RHF else buf[2])
 
 
     # ------------------------------------------------------------------ batched J/K (NOCI)

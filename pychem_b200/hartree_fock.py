@@ -69,7 +69,8 @@ def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
         mref = weakref.ref(molecule)
     except TypeError:
         mref = (lambda m: (lambda: m))(molecule)
-    st = {"mode": mode, "db": db, "G_dev": None, "molecule": mref}
+    st = {"mode": mode, "db": db, "G_dev": None, "molecule": mref,
+          "key": (getattr(molecule, "Basis", None), int(molecule.NOrbitals), len(molecule.Atoms))}
     if mode == "stored":
         G_dev, G_host = db.eri_tensor(engine.INTEGRAL_THRESHOLD, to_host=True)
         st["G_dev"] = G_dev
@@ -112,8 +113,14 @@ def _state_for(molecule):
     to an earlier geometry / basis of the same object (integrals.device_basis hands out a new
     DeviceBasis then) or was left on the scattering integrals by a property job."""
     st = _STATE.get(id(molecule))
-    if (st is None or st["molecule"]() is not molecule or st["db"].h is None
-            or st["db"] is not device_basis(molecule) or st["db"].ints_type != 0):
+    # Per Fock build only the cheap part of the check: same object, live handle, repulsion integrals,
+    # same basis label and size.  The full stamp (every atom's coordinates, integrals._stamp: 0.17 ms
+    # of host time at 96 atoms, paid before anything is queued on the device) is compared where the
+    # reference recomputes its integrals too: in evaluate_2e_ints, which hartree_fock.do calls once
+    # per SCF (Methods/hartree_fock.py:32) -- a geometry edited in place WITHOUT that call is stale
+    # in the reference as well (molecule.CoulombIntegrals).
+    if (st is None or st["molecule"]() is not molecule or st["db"].h is None or st["db"].ints_type != 0
+            or st["key"] != (getattr(molecule, "Basis", None), int(molecule.NOrbitals), len(molecule.Atoms))):
         evaluate_2e_ints(molecule)
         st = _STATE[id(molecule)]
     return st

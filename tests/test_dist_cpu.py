@@ -94,3 +94,53 @@ def test_two_rank_partition_allreduce_finalize(general):
         p.join(180)
         assert p.exitcode == 0
     assert out.get(timeout=5) < 1e-11
+
+
+# ---------------------------------------------------------------------------------------------
+# NodeShare: the host buffer the ranks of one node share for the results (pychem_b200/dist.py)
+# ---------------------------------------------------------------------------------------------
+def _share_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init("gloo")
+    N = 37                                     # not a multiple of the world size: ragged last slice
+    sh = dist.NodeShare((3, N, N), pin=False)
+    lo, hi = sh.rows(N)
+    ok = True
+    for call in range(5):                      # more calls than buffers: the rotation is exercised
+        full = np.arange(3 * N * N, dtype=float).reshape(3, N, N) + 1000.0 * call
+        buf = sh.buffer()
+        buf[:, lo:hi] = full[:, lo:hi]          # this rank's rows only
+        if rank == 1:
+            import time
+            time.sleep(0.02 * (call % 2))      # skewed arrival at the barrier
+        sh.barrier()
+        ok = ok and bool((buf == full).all())  # everybody sees everybody's rows
+        prev = buf
+    # the previous call's view is still intact while the next buffer is being filled
+    nxt = sh.buffer()
+    nxt[:, lo:hi] = -1.0
+    ok = ok and bool((prev == full).all()) and nxt is not prev
+    sh.barrier()
+    rows = [None] * world
+    tdist.all_gather_object(rows, (lo, hi))
+    if rank == 0:
+        covered = sorted(rows)
+        ok = ok and covered[0][0] == 0 and covered[-1][1] == N and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+        out.put(ok)
+    sh.close()
+    tdist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_node_share_publishes_row_slices_to_every_rank(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_share_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert out.get(timeout=10) is True
