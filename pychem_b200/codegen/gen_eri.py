@@ -347,16 +347,6 @@ class ClassGen:
             s.append("  double2 n0 = __ldg(brec + 3), n1 = __ldg(brec + 4), n2 = __ldg(brec + 5);")
         s.append("  for (int ik = 0; ik < KK; ++ik, kp += 3 * (size_t)nk) {")
         s.extend("    " + l for l in ket_load)
-        if self.L <= BOYS_PF_MAXL:
-            # first pass over the bra primitives of this ket primitive: Boys rows into L1
-            s.append("    if (!(MODE == PC_MODE_BLOCKS_SCAT || MODE == PC_MODE_TENSOR_SCAT)) {")
-            s.append("      const double2* __restrict__ bq2 = brec + 3;")
-            s.append("      for (int ib = 0; ib < KB; ++ib, bq2 += 3) {")
-            s.append("        const double2 t0 = __ldg(bq2), t1 = __ldg(bq2 + 1), t2 = __ldg(bq2 + 2);")
-            s.append("        const double dx = t1.x - Qx, dy = t1.y - Qy, dz = t2.x - Qz;")
-            s.append("        pc_boys_prefetch<L>(t0.x, sQ, dx * dx + dy * dy + dz * dz, A.boys);")
-            s.append("      }")
-            s.append("    }")
         s.append("    const double2* __restrict__ bq = brec + 3;")
         if UNROLL_IB > 1 and self.L <= UNROLL_IB_MAXL and not self.V2:
             s.append("#pragma unroll %d" % UNROLL_IB)
@@ -1135,11 +1125,9 @@ if os.environ.get("PC_GEN_COOP"):
 # bra-record prefetch: 0 = none (the record's lines hit L1 after the first touch), 1 = next primitive
 # one iteration ahead in registers, 2 = prefetch.global.L1 of the record's lines at task start
 PREFETCH = int(os.environ.get("PC_GEN_PREFETCH", "0"))
-# experiment: classes with L <= this prefetch the Boys rows of the next bra-primitive loop into L1
 # experiment: unroll the bra-primitive loop (the loads of the next primitive can be scheduled early)
 UNROLL_IB = int(os.environ.get("PC_GEN_UNROLL_IB", "1"))
 UNROLL_IB_MAXL = int(os.environ.get("PC_GEN_UNROLL_IB_MAXL", "3"))
-BOYS_PF_MAXL = int(os.environ.get("PC_GEN_BOYS_PF_MAXL", "-1"))
 FUSE_ACC = os.environ.get("PC_GEN_FUSE_ACC", "1") != "0"
 V2_THRESHOLD = int(os.environ.get("PC_GEN_V2_THRESHOLD", "650"))   # classes with more VRR temporaries than this use the rolled form
 

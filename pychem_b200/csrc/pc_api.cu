@@ -181,7 +181,8 @@ struct pc_basis {
   std::vector<double> prim_host; // per pair, most significant primitive first: {sigma, Ucc, Px, Py, Pz, kz}
   std::vector<Kind*> kinds;
   DevBuf<double> boys;                  // [m][j][4]  (one-electron kernel)
-  DevBuf<double> boys_l[4 * PCG_LMAX + 1];   // per total angular momentum L: [j][m = 0..L][4] (ERI kernels)
+  DevBuf<double> boys_l[4 * PCG_LMAX + 1];   // per total angular momentum L < PC_BOYS_COMPACT_MINL: [j][m = 0..L][4]
+  DevBuf<double> boys_c[3];             // compact rows of 8 / 12 / 16 values H_k = F_k h^k (L <= 4 / 8 / 12)
   int max_l = 0;                        // highest shell angular momentum of the molecule
   bool force_generic = false;           // PYCHEM_B200_FORCE_GENERIC=1: every class takes the generic kernel (tests)
   DevBuf<double> gen_scratch;           // scratch of the generic kernel for explicit task lists
@@ -451,7 +452,10 @@ int gen_thread_count(long long nwarps, size_t words) {
 // handle's own buffer, grown on demand (explicit task lists, all on h->stream)
 cudaError_t launch_args(pc_basis* h, int mode, int pcb, int pck, PcEriArgs& A, cudaStream_t st,
                         DevBuf<double>* scratch = nullptr, int gen_threads = 0) {
-  A.boys = h->boys_l[pair_L(pcb) + pair_L(pck)].p;
+  {
+    const int Lq = pair_L(pcb) + pair_L(pck);
+    A.boys = Lq < PC_BOYS_COMPACT_MINL ? h->boys_l[Lq].p : h->boys_c[pc_boys_row(Lq) / 4 - 2].p;
+  }
   A.nbf = h->nbf;
   A.scat_S = h->grid;
   A.thresh = h->thresh;
@@ -731,7 +735,7 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
   // The ERI kernels of one class read the orders m = 0..L of ONE interval: per-L copies with the
   // orders of an interval adjacent ((L+1) x 32 bytes contiguous) cost one cache line per lookup
   // instead of L+1 lines 248 KB apart.
-  for (int L = 0; L <= 4 * h->max_l && e == cudaSuccess; ++L) {
+  for (int L = 0; L <= 4 * h->max_l && L < PC_BOYS_COMPACT_MINL && e == cudaSuccess; ++L) {
     std::vector<double> t((size_t)PC_BOYS_NPOINTS * (L + 1) * 4);
     for (int j = 0; j < PC_BOYS_NPOINTS; ++j)
       for (int m = 0; m <= L; ++m)
@@ -739,6 +743,18 @@ int pc_basis_create(int device, int nshell, const int* l, const int* K, const in
           t[((size_t)j * (L + 1) + m) * 4 + c] = tab[((size_t)m * PC_BOYS_NPOINTS + j) * 4 + c];
     e = h->boys_l[L].upload(t, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);     // `t` dies here
+  }
+  // From L = PC_BOYS_COMPACT_MINL on the classes share compact rows: L + 4 scaled values per grid
+  // point (one 496 KB table for L <= 4, 744 KB for L <= 8, 992 KB with f shells) instead of per-L
+  // copies of 4 (L + 1) coefficients (744 KB ... 3.2 MB each): 2 / 3 / 4 sectors per lookup.
+  for (int t = 0; t < 3 && e == cudaSuccess; ++t) {
+    const int row = 8 + 4 * t, lmax = 4 * (t + 1);
+    if (4 * h->max_l <= lmax - 4 && t > 0) break;                   // no class needs the longer rows
+    if (4 * h->max_l < PC_BOYS_COMPACT_MINL) break;
+    std::vector<double> v((size_t)PC_BOYS_NPOINTS * row);
+    pcb_make_scaled_values(row, v.data());
+    e = h->boys_c[t].upload(v, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);     // `v` dies here
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) { delete h; return fail(cudaGetErrorString(e)); }

@@ -12,7 +12,6 @@ g++ cannot take as they are:
   kernel<<<grid, block, smem, stream>>>(args);  ->  pcemu::launch(grid, block, [&] { kernel(args); });
   the inline-PTX reciprocal-square-root seed    ->  pcemu::rsqrt_seed(x)
   the inline-PTX L1 prefetch                    ->  nothing
-  the inline-PTX 256-bit table load             ->  four plain loads
 pc_mp2.cu (inline-PTX mma.sync) is not emulated; its three entry points report an error.
 """
 import hashlib
@@ -37,7 +36,6 @@ CXX_FLAGS = ["-std=c++17", "-O1", "-fPIC", "-mfma", "-DPC_HOST_EMU=1", "-w",
 LAUNCH = re.compile(r"([A-Za-z_][\w:]*(?:<[^<>;()]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
 RSQRT_ASM = 'asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));'
 PREFETCH_ASM = 'asm volatile("prefetch.global.L1 [%0];" ::"l"(p));'
-LDG256_ASM = 'asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));'
 
 MP2_STUB = r'''
 // pc_mp2.cu is not emulated (inline-PTX mma.sync): the entry points exist and fail loudly
@@ -76,15 +74,11 @@ def transform(text, name):
         return "pcemu::launch((unsigned)(%s), (unsigned)(%s), [&] { %s(%s); });" % (cfg[0], cfg[1], kern, args)
     # real-PTX regions that have a functional model under PC_HOST_EMU (pc_async.cuh)
     text = re.sub(r"// PC_EMU_SKIP_BEGIN.*?// PC_EMU_SKIP_END", "", text, flags=re.S)
-    text = text.replace('asm volatile("prefetch.global.L1 [%0];" ::"l"(row));', "(void)row;")
-    text = text.replace('asm volatile("prefetch.global.L1 [%0];" ::"l"(row + 128));', "(void)row;")
-    text = text.replace("__frcp_rn((float)sPQ)", "(1.0f / (float)sPQ)")
     text, n = LAUNCH.subn(repl, text)
     if name == "pc_common.cuh":
-        if RSQRT_ASM not in text or PREFETCH_ASM not in text or LDG256_ASM not in text:
+        if RSQRT_ASM not in text or PREFETCH_ASM not in text:
             raise RuntimeError("build_emu: the inline-PTX statements of pc_common.cuh changed; update build_emu.py")
-        text = text.replace(RSQRT_ASM, "y = pcemu::rsqrt_seed(x);").replace(PREFETCH_ASM, "(void)p;").replace(
-            LDG256_ASM, "v.x = p[0]; v.y = p[1]; v.z = p[2]; v.w = p[3];")
+        text = text.replace(RSQRT_ASM, "y = pcemu::rsqrt_seed(x);").replace(PREFETCH_ASM, "(void)p;")
     if "<<<" in text or "asm(" in text.replace(" ", "") or "asmvolatile(" in text.replace(" ", ""):
         raise RuntimeError("build_emu: %s still holds CUDA-only syntax after the substitutions" % name)
     return text
