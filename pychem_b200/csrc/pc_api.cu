@@ -287,6 +287,8 @@ void compute_pair_prims(pc_basis* h) {
   const double lnorm[4] = {pi34, std::sqrt(2.0) * pi34, 2.0 * pi34, 2.0 * std::sqrt(2.0) * pi34};
   const double pf_half = std::pow(2.0 / M_PI, 0.25) * std::pow(2.0, 0.25);   // ... and the sqrt(2) of sqrt(2 theta^2)
   const size_t chunk = 256;
+  // PYCHEM_B200_PRIM_EPS: measurement knob for the cut-off (default PC_PRIM_EPS)
+  const double prim_eps = []() { const char* e = getenv("PYCHEM_B200_PRIM_EPS"); return e ? atof(e) : PC_PRIM_EPS; }();
   parallel_for((h->pairs.size() + chunk - 1) / chunk, [&](size_t c) {
     struct PP { double sigma, ucc, P[3], kz; };
     std::vector<PP> pp;
@@ -319,7 +321,7 @@ void compute_pair_prims(pc_basis* h) {
       std::stable_sort(pp.begin(), pp.end(), [](const PP& u, const PP& v) { return std::fabs(u.ucc) > std::fabs(v.ucc); });
       const int K = (int)pp.size();
       int ke = 0;
-      while (ke < K && std::fabs(pp[ke].ucc) >= PC_PRIM_EPS) ++ke;
+      while (ke < K && std::fabs(pp[ke].ucc) >= prim_eps) ++ke;
       p.keff = std::max(ke, 1);
       double* o = &h->prim_host[p.prim_off * 6];
       for (int q = 0; q < K; ++q, o += 6) {
