@@ -213,6 +213,9 @@ struct pc_basis {
   // (they only meet in the atomics), so they are spread round-robin to overlap their tails
   std::vector<cudaStream_t> side;
   cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_flag = nullptr;        // classification flag has reached flag_host
+  int* flag_host = nullptr;             // page-locked
+  int guess_variant = 0;                // variant of the previous auto call (speculative digestion)
   std::vector<cudaEvent_t> ev_join;
   // the launch sequence of one Fock build, captured once per (variant, buffers, plan) and
   // replayed as a CUDA graph: removes the host launch cost of ~200 kernels per build
@@ -242,6 +245,8 @@ struct pc_basis {
     for (auto e : prof_events) cudaEventDestroy(e);
     for (auto e : ev_join) cudaEventDestroy(e);
     if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_flag) cudaEventDestroy(ev_flag);
+    if (flag_host) cudaFreeHost(flag_host);
     for (auto st : side) cudaStreamDestroy(st);
     for (auto* k : kinds) delete k;
     for (auto* b : gen_bufs) delete b;
@@ -1403,18 +1408,47 @@ int pc_jk_classify(pc_basis* h, const double* Dt, const double* Da, const double
   return 0;
 }
 
+// Classify on the device and digest straight from the staged copies (one upload only).  The
+// 4-byte flag needs a host round trip before the right digestion kernels can be chosen; an SCF
+// hands over the same kind of densities call after call, so the digestion of the PREVIOUS call's
+// variant is queued behind the classification at once and the host reads the flag while it runs.
+// A different answer (first call of another kind) queues the right digestion after it -- the
+// accumulators are cleared by every pc_jk_direct_accumulate.  PYCHEM_B200_SPECULATE=0: wait first.
+static int classify_then_accumulate(pc_basis* h, const double* Dt, const double* Da, const double* Db,
+                                    double* acc_dev, int* variant) {
+  if (!Db) Db = Da;
+  const size_t nn = (size_t)h->nbf * h->nbf;
+  const double *dt, *da, *db;
+  if (stage_in(h, Dt, h->dstage.p, &dt) || stage_in(h, Da, h->dstage.p + nn, &da) ||
+      stage_in(h, Db, h->dstage.p + 2 * nn, &db)) return 1;
+  if (!h->flags.p) PC_CUDA(h->flags.alloc(1));
+  if (!h->flag_host) PC_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->flag_host), sizeof(int)));
+  if (!h->ev_flag) PC_CUDA(cudaEventCreateWithFlags(&h->ev_flag, cudaEventDisableTiming));
+  PC_CUDA(cudaMemsetAsync(h->flags.p, 0, sizeof(int), h->stream));
+  const int blocks = (int)std::min<size_t>((nn + 255) / 256, 148 * 8);
+  classify_kernel<<<blocks, 256, 0, h->stream>>>(h->nbf, dt, da, db, h->flags.p);
+  PC_CUDA(cudaGetLastError());
+  h->launches += 1;
+  PC_CUDA(cudaMemcpyAsync(h->flag_host, h->flags.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PC_CUDA(cudaEventRecord(h->ev_flag, h->stream));
+  static const bool speculate = []() { const char* e = getenv("PYCHEM_B200_SPECULATE"); return !(e && e[0] == '0'); }();
+  const int guess = speculate ? h->guess_variant : 0;
+  if (guess && pc_jk_direct_accumulate(h, guess, dt, da, db, acc_dev)) return 1;
+  PC_CUDA(cudaEventSynchronize(h->ev_flag));
+  const int f = *h->flag_host;
+  const int v = (f & 1) ? PC_JK_GEN : ((f & 2) ? PC_JK_UHF : PC_JK_RHF);
+  if (v != guess && pc_jk_direct_accumulate(h, v, dt, da, db, acc_dev)) return 1;
+  h->guess_variant = v;
+  *variant = v;
+  return 0;
+}
+
 int pc_jk_direct_accumulate_auto(pc_basis* h, const double* Dt, const double* Da, const double* Db,
                                  double* acc_dev, int* variant) {
   if (!h || !variant) return fail("pc_jk_direct_accumulate_auto: null");
   PC_CUDA(cudaSetDevice(h->device));
   if (ensure_scratch(h)) return 1;
-  // classify on the device, then digest straight from the staged copies (one upload only)
-  if (pc_jk_classify(h, Dt, Da, Db, variant)) return 1;
-  const size_t nn = (size_t)h->nbf * h->nbf;
-  if (!is_device_ptr(Dt)) Dt = h->dstage.p;
-  if (!is_device_ptr(Da)) Da = h->dstage.p + nn;
-  if (Db && !is_device_ptr(Db)) Db = h->dstage.p + 2 * nn;
-  return pc_jk_direct_accumulate(h, *variant, Dt, Da, Db, acc_dev);
+  return classify_then_accumulate(h, Dt, Da, Db, acc_dev, variant);
 }
 
 int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, const double* Db,
@@ -1423,12 +1457,8 @@ int pc_jk_direct(pc_basis* h, int variant, const double* Dt, const double* Da, c
   PC_CUDA(cudaSetDevice(h->device));
   if (ensure_scratch(h)) return 1;
   if (variant == PC_JK_AUTO) {
-    // classify on the device, then digest straight from the staged copies (no second upload)
-    if (pc_jk_classify(h, Dt, Da, Db, &variant)) return 1;
-    const size_t nn = (size_t)h->nbf * h->nbf;
-    if (!is_device_ptr(Dt)) Dt = h->dstage.p;
-    if (!is_device_ptr(Da)) Da = h->dstage.p + nn;
-    if (Db && !is_device_ptr(Db)) Db = h->dstage.p + 2 * nn;
+    if (classify_then_accumulate(h, Dt, Da, Db, h->acc.p, &variant)) return 1;
+    return pc_jk_finalize(h, variant, h->acc.p, J, Xa, Xb);
   }
   if (pc_jk_direct_accumulate(h, variant, Dt, Da, Db, h->acc.p)) return 1;
   return pc_jk_finalize(h, variant, h->acc.p, J, Xa, Xb);
@@ -1439,13 +1469,7 @@ int pc_jk_direct_auto(pc_basis* h, const double* Dt, const double* Da, const dou
   if (!h || !variant) return fail("pc_jk_direct_auto: null");
   PC_CUDA(cudaSetDevice(h->device));
   if (ensure_scratch(h)) return 1;
-  // classify on the device, then digest straight from the staged copies (one upload only)
-  if (pc_jk_classify(h, Dt, Da, Db, variant)) return 1;
-  const size_t nn = (size_t)h->nbf * h->nbf;
-  if (!is_device_ptr(Dt)) Dt = h->dstage.p;
-  if (!is_device_ptr(Da)) Da = h->dstage.p + nn;
-  if (Db && !is_device_ptr(Db)) Db = h->dstage.p + 2 * nn;
-  if (pc_jk_direct_accumulate(h, *variant, Dt, Da, Db, h->acc.p)) return 1;
+  if (classify_then_accumulate(h, Dt, Da, Db, h->acc.p, variant)) return 1;
   // closed-shell densities: X_beta == X_alpha, nothing is copied into Xb
   return pc_jk_finalize(h, *variant, h->acc.p, J, Xa, *variant == PC_JK_RHF ? nullptr : Xb);
 }

@@ -395,3 +395,24 @@ def test_emu_direct_jk_vs_sampled_oracle_rows(emu):
         assert np.abs(Xa - Xa0)[mX].max() < JK_TOL
         assert np.abs(Xb - Xb0)[mX].max() < JK_TOL
     db.close()
+
+
+def test_emu_auto_variant_speculation(emu):
+    """pc_jk_direct with PC_JK_AUTO queues the digestion of the previous call's variant behind the
+    classification kernel and repeats it when the flag says otherwise: alternate closed-shell,
+    general, closed-shell, open-shell densities and compare every result with the explicit call."""
+    from pychem_b200 import structures as S
+    db = emu.EmuBasis(S.Molecule(S.water_cluster(1), "6-31G**"))
+    db.plan(1.0e-8, 0, 1)
+    rng = np.random.default_rng(5)
+    N = db.nbf
+    Da, Db = _sym(rng, N), _sym(rng, N)
+    A, B = rng.uniform(-1, 1, (N, N)), rng.uniform(-1, 1, (N, N))
+    seq = [(2 * Da, Da, Da, emu.RHF), (A + B, A, B, emu.GEN), (2 * Da, Da, Da, emu.RHF), (2 * Da, Da, Da, emu.RHF),
+           (Da + Db, Da, Db, emu.UHF), (A + B, A, B, emu.GEN)]
+    for Dt, D1, D2, variant in seq:
+        auto = db.jk_direct(Dt, D1, D2)                       # AUTO
+        ref = db.jk_direct(Dt, D1, D2, variant=variant)
+        for x, y in zip(auto, ref):
+            assert np.abs(x - y).max() < 1.0e-13
+    db.close()
