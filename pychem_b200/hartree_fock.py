@@ -70,7 +70,7 @@ def evaluate_2e_ints(molecule, ints_type=0, grid_value=-1.0):
     except TypeError:
         mref = (lambda m: (lambda: m))(molecule)
     st = {"mode": mode, "db": db, "G_dev": None, "molecule": mref,
-          "key": (getattr(molecule, "Basis", None), int(molecule.NOrbitals), len(molecule.Atoms))}
+          "key": _quick_key(molecule)}
     if mode == "stored":
         G_dev, G_host = db.eri_tensor(engine.INTEGRAL_THRESHOLD, to_host=True)
         st["G_dev"] = G_dev
@@ -114,16 +114,25 @@ def _state_for(molecule):
     DeviceBasis then) or was left on the scattering integrals by a property job."""
     st = _STATE.get(id(molecule))
     # Per Fock build only the cheap part of the check: same object, live handle, repulsion integrals,
-    # same basis label and size.  The full stamp (every atom's coordinates, integrals._stamp: 0.17 ms
+    # same basis label and size, same coordinate checksum.  The full stamp (integrals._stamp: 0.17 ms
     # of host time at 96 atoms, paid before anything is queued on the device) is compared where the
     # reference recomputes its integrals too: in evaluate_2e_ints, which hartree_fock.do calls once
-    # per SCF (Methods/hartree_fock.py:32) -- a geometry edited in place WITHOUT that call is stale
-    # in the reference as well (molecule.CoulombIntegrals).
+    # per SCF (Methods/hartree_fock.py:32).
     if (st is None or st["molecule"]() is not molecule or st["db"].h is None or st["db"].ints_type != 0
-            or st["key"] != (getattr(molecule, "Basis", None), int(molecule.NOrbitals), len(molecule.Atoms))):
+            or st["key"] != _quick_key(molecule)):
         evaluate_2e_ints(molecule)
         st = _STATE[id(molecule)]
     return st
+
+
+def _quick_key(molecule):
+    """Basis label, sizes and a weighted checksum of the coordinates: ~30 us at 96 atoms, catches a
+    geometry edited in place (Atom.update_coords, Util/structures.py:827) between Fock builds."""
+    chk = 0.0
+    for k, a in enumerate(molecule.Atoms):
+        c = a.Coordinates
+        chk += (k + 1) * (c[0] + 2.0 * c[1] + 3.0 * c[2])
+    return (getattr(molecule, "Basis", None), int(molecule.NOrbitals), len(molecule.Atoms), chk)
 
 
 def make_coulomb_exchange_matrices(molecule, this):

@@ -207,3 +207,20 @@ def test_plan_segments_cover_reference_loop_nest(run, same):
             assert cnt == q[s + 1] - q[s]
         assert len(got) == len(set(got)), "a quartet was produced twice"
         assert set(got) == want
+
+
+def test_state_key_follows_in_place_geometry_edits():
+    """hartree_fock._quick_key (checked before every Fock build) changes when an atom is moved in
+    place, when atoms are swapped, and with the basis label; it is stable otherwise."""
+    from pychem_b200 import hartree_fock as hf, structures as S
+    mol = S.Molecule(S.water_cluster(2), "6-31G**")
+    k0 = hf._quick_key(mol)
+    assert hf._quick_key(mol) == k0
+    saved = list(mol.Atoms[3].Coordinates)
+    mol.Atoms[3].Coordinates[1] += 1.0e-6
+    assert hf._quick_key(mol) != k0
+    mol.Atoms[3].Coordinates[1] = saved[1]
+    assert hf._quick_key(mol) == k0
+    a, b = mol.Atoms[1].Coordinates, mol.Atoms[2].Coordinates           # two hydrogens trade places
+    mol.Atoms[1].Coordinates, mol.Atoms[2].Coordinates = b, a
+    assert hf._quick_key(mol) != k0
