@@ -569,6 +569,20 @@ class ClassGen:
         s.append("  if (MODE >= PC_MODE_JK_RHF && MODE <= PC_MODE_JK_GEN)")
         s.append("    pc_prefetch_density<%s>(A, fa, fb, __ldg(I.ket.fx + j), __ldg(I.ket.fy + j), MODE != PC_MODE_JK_GEN);" % dims)
         s.append("  const double CD0 = __ldg(I.ket.xy + j), CD1 = __ldg(I.ket.xy + nk + j), CD2 = __ldg(I.ket.xy + 2 * nk + j);")
+        self.emit_body(s, nmax, vrr, tail)
+        s.append("  pc_epilogue<MODE, %s>(A, I, t, valid, fa, fb, pidb, j, seg_lo, seg_hi, g, S);" % dims)
+        s.append("}")
+        self.coop = None
+        if self.name in COOP_CLASSES and not self.cart_d:
+            self.coop = CoopGen(self, COOP_CLASSES[self.name])
+            s.extend(self.coop.source())
+        s.append("}  // namespace")
+        s.append("")
+        s.extend(self.launcher(block))
+        return "\n".join(s) + "\n"
+
+    def emit_body(self, s, nmax, vrr, tail):
+        """primitive loops + contraction + tail: leaves g[NSPH]"""
         s.append("  double acc[NE * NF];")
         s.append("#pragma unroll%s" % (" 1" if self.V2 else ""))
         s.append("  for (int k = 0; k < NE * NF; ++k) acc[k] = 0.0;")
@@ -581,22 +595,80 @@ class ClassGen:
         s.append("  double g[NSPH];")
         for line in tail:
             s.append("  " + line)
-        s.append("  pc_epilogue<MODE, %s>(A, I, t, valid, fa, fb, pidb, j, seg_lo, seg_hi, g, S);" % dims)
-        s.append("}")
-        self.coop = None
-        if self.name in COOP_CLASSES and not self.cart_d:
-            self.coop = CoopGen(self, COOP_CLASSES[self.name])
-            s.extend(self.coop.source())
-        s.append("}  // namespace")
-        s.append("")
-        s.extend(self.launcher(block))
-        return "\n".join(s) + "\n"
 
     def tables(self):
         return []
 
     def scratch_decls(self):
         return []
+
+
+class ClassGenPass(ClassGen):
+    """Several passes over the primitive loops, one per group of bra components (the grouping of
+    CoopGen: chains of the bra recursion, dealt out by cost).  A pass keeps only ITS ne_p x nf
+    contracted accumulators -- in registers -- and ends with the ket HRR + cart->spherical of its
+    (e0| rows, written once per quartet to the per-thread array ks[]; the bra HRR, the bra
+    cart->spherical and the digestion follow as in the one-pass form.  The one-pass kernels of these
+    classes keep 144-279 accumulators in local memory and touch them in every primitive quartet
+    ((dp|pp): 126 local stores + 151 loads per primitive quartet, 1.1 GB of DRAM writes per launch);
+    here the price is the shared low end of the recursion, computed once per pass."""
+
+    def __init__(self, *cls, **kw):
+        self.npass = kw.pop("npass", 3)
+        ClassGen.__init__(self, *cls, **kw)
+        self.groups = CoopGen(self, self.npass, ket_split=False)
+
+    def emit_body(self, s, nmax, vrr, tail):
+        co = self.groups
+        lx1, ly1, lx2, ly2 = self.l
+        NA, NB, NC, ND = self.nsph
+        nq = NC * ND
+        s.append("  double ks[%d];      // (e0|cd): ket HRR + cart->spherical done, [e][q]" % (self.ne * nq))
+        for r, es in enumerate(co.egroups):
+            s.append("  {   // pass %d: bra components %s" % (r, " ".join("%d%d%d" % e for e in es)))
+            s.append("  double acc[%d];" % (len(es) * self.nf))
+            s.append("#pragma unroll")
+            s.append("  for (int k = 0; k < %d; ++k) acc[k] = 0.0;" % (len(es) * self.nf))
+            self.prim_prologue(s, nmax)
+            for line in co.sub(es).gen_vrr():
+                s.append("      " + line)
+            self.close_prim_loops(s)
+            for line in co.ket_tail(r, dest="ks[%d]", lane_stride=1):
+                s.append("  " + line)
+            s.append("  }")
+        s.append("  (void)AB0; (void)AB1; (void)AB2; (void)CD0; (void)CD1; (void)CD2;")
+        s.append("  double g[NSPH];")
+        # bra HRR + cart->spherical for every ket function pair q, from ks[]
+        em = Emit("hb")
+        e_glob = {c: i for i, c in enumerate(self.e_list)}
+        out = []
+        for q in range(nq):
+            memo = {}
+
+            def hb(cx, cy):
+                key = (cx, cy)
+                if key in memo:
+                    return memo[key]
+                if sum(cy) == 0:
+                    val = "ks[%d]" % (e_glob[cx] * nq + q)
+                else:
+                    d = first_dir(cy)
+                    cy0 = dec(cy, d)
+                    val = em.new("fma(AB%d, %s, %s)" % (d, hb(cx, cy0), hb(inc(cx, d), cy0)))
+                memo[key] = val
+                return val
+
+            cart = {(ix, iy): hb(cx, cy) for ix, cx in enumerate(comps(lx1)) for iy, cy in enumerate(comps(ly1))}
+            half = {}
+            for ix in range(ncart(lx1)):
+                for my, row in enumerate(c2s_rows(ly1)):
+                    half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
+            for mx, row in enumerate(c2s_rows(lx1)):
+                for my in range(nsph(ly1)):
+                    v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
+                    out.append("g[%d] = %s;" % ((mx * nsph(ly1) + my) * nq + q, v))
+        for line in em.lines + out:
+            s.append("  " + line)
 
 
 class ClassGenV2(ClassGen):
@@ -869,14 +941,14 @@ class CoopGen:
 
     MODES = ("PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL")
 
-    def __init__(self, base, G):
+    def __init__(self, base, G, ket_split=True):
         self.b = base
         lx1, ly1, lx2, ly2 = base.l
         NA, NB, NC, ND = base.nsph
         split = os.environ.get("PC_GEN_COOP_SPLIT", "d")          # phase 2 by ket function d (default) or c
         if ND == 1:
             split = "c"
-        self.G = G = min(G, ND if split == "d" else NC, ncart(lx1))
+        self.G = G = min(G, (ND if split == "d" else NC) if ket_split else G, ncart(lx1))
         self.nq = NC * ND
 
         def anc(e):
@@ -916,8 +988,8 @@ class CoopGen:
         g.ne = len(es)
         return g
 
-    def ket_tail(self, r):
-        """ket HRR + cart->spherical of role r's (e0| rows; results to shared memory."""
+    def ket_tail(self, r, dest="ks_sm[%d + lane]", lane_stride=32):
+        """ket HRR + cart->spherical of role r's (e0| rows; results to shared memory (or `dest`)."""
         b = self.b
         lx1, ly1, lx2, ly2 = b.l
         em = Emit("hk")
@@ -949,7 +1021,7 @@ class CoopGen:
                 for my in range(nsph(ly2)):
                     v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
                     q = mx * nsph(ly2) + my
-                    out.append("ks_sm[%d + lane] = %s;" % ((e_glob[e] * self.nq + q) * 32, v))
+                    out.append("%s = %s;" % (dest % ((e_glob[e] * self.nq + q) * lane_stride), v))
         return em.lines + out
 
     def bra_tail(self, r):
@@ -1116,6 +1188,12 @@ class CoopGen:
         return s
 
 
+# classes built in the multi-pass form (ClassGenPass) and their number of passes: measured on
+# (H2O)32 (profiles/r2g_multipass_high_l.txt); (dd|ps), (pp|pp), (dp|ps) and (dd|dd) lose with it
+PASS_CLASSES = {"dppp": 2, "dpdp": 3, "dpds": 2, "ddds": 3, "ddpp": 4, "dddp": 6}
+if os.environ.get("PC_GEN_PASS") is not None:
+    PASS_CLASSES = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in os.environ["PC_GEN_PASS"].split(",") if kv and kv != "0")
+
 # classes built in the warp-cooperative form as well, and their number of roles
 COOP_CLASSES = {}
 if os.environ.get("PC_GEN_COOP"):
@@ -1156,6 +1234,8 @@ SKIP_CART = os.environ.get("PC_GEN_SKIP_CART", "0") != "0"
 
 def make_class(cls, cart_d=False):
     g = ClassGen(*cls, cart_d=cart_d)
+    if g.name in PASS_CLASSES and not g.cart_d:
+        return ClassGenPass(*cls, npass=PASS_CLASSES[g.name])
     g.gen_vrr()
     if g.n_vrr > V2_THRESHOLD:
         return ClassGenV2(*cls, cart_d=cart_d)
