@@ -1,11 +1,11 @@
 #!/bin/bash
-O=gpurun_out/r2c23
+O=gpurun_out/r2c26
 mkdir -p $O; rm -f $O/*
 V=pychem_b200/variants
-timeout 1500 python tools/ab_classes.py --reps 3 --check cur=$V/lib_cur.so P1=$V/lib_P1.so P2=$V/lib_P2.so P3=$V/lib_P3.so P4=$V/lib_P4.so > $O/ab.jsonl 2> $O/ab.err; echo "ab rc=$?"
+timeout 1500 python tools/ab_classes.py --reps 3 --check cur=$V/lib_cur.so M5=$V/lib_M5.so M6=$V/lib_M6.so D8=$V/lib_D8.so D9=$V/lib_D9.so > $O/ab.jsonl 2> $O/ab.err; echo "ab rc=$?"
 python - <<'PY'
 import json
-rows=[json.loads(l) for l in open('gpurun_out/r2c23/ab.jsonl')]
+rows=[json.loads(l) for l in open('gpurun_out/r2c26/ab.jsonl')]
 rows=[r for r in rows if 'error' not in r]
 names=[r['name'] for r in rows]
 print('variant   wall    jk_total gen_total  dJ dX')

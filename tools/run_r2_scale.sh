@@ -6,8 +6,8 @@ nvidia-smi -L | wc -l
 [ -z "$WITH_TESTS" ] || { timeout 600 python -m pytest tests/test_gpu_mp2.py -m gpu -q -x > $O/tests.log 2>&1; tail -3 $O/tests.log; }
 # N > 1: host traffic sharded over the ranks (default); PYCHEM_B200_SHARED_RESULTS=0 for whole matrices per rank
 TR8="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513"
-timeout 600 $TR8 tools/check_share_ngpu.py > $O/check_share_8.json 2> $O/check_share_8.err; echo "share check rc=$?"; cat $O/check_share_8.json
-PYCHEM_B200_SHARED_RESULTS=0 timeout 600 $TR8 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline --no-stored --sweep 32 > $O/bench_8_unshared.json 2> $O/bench_8_unshared.err
+[ -n "$SKIP_SHARE_CHECK" ] || timeout 600 $TR8 tools/check_share_ngpu.py > $O/check_share_8.json 2> $O/check_share_8.err; echo "share check rc=$?"; cat $O/check_share_8.json
+[ -n "$SKIP_SHARE_CHECK" ] || PYCHEM_B200_SHARED_RESULTS=0 timeout 600 $TR8 bench.py --gpus 8 --steps 20 --warmup 3 --no-cpu-baseline --no-stored --sweep 32 > $O/bench_8_unshared.json 2> $O/bench_8_unshared.err
 python - <<PY
 import json
 try:
