@@ -616,7 +616,11 @@ class ClassGenPass(ClassGen):
     def __init__(self, *cls, **kw):
         self.npass = kw.pop("npass", 3)
         ClassGen.__init__(self, *cls, **kw)
-        self.groups = CoopGen(self, self.npass, ket_split=False)
+        if isinstance(self.npass, str):           # "c96": as many passes as a cap of 96 accumulators per pass needs
+            self.groups = CoopGen(self, 2, ket_split=False)
+            self.groups.regroup_by_cap(int(self.npass[1:]))
+        else:
+            self.groups = CoopGen(self, self.npass, ket_split=False)
 
     def emit_body(self, s, nmax, vrr, tail):
         co = self.groups
@@ -941,18 +945,20 @@ class CoopGen:
 
     MODES = ("PC_MODE_JK_RHF", "PC_MODE_JK_UHF", "PC_MODE_JK_GEN", "PC_MODE_NULL")
 
-    def __init__(self, base, G, ket_split=True):
+    def __init__(self, base, G, ket_split=True, depth=0):
         self.b = base
         lx1, ly1, lx2, ly2 = base.l
         NA, NB, NC, ND = base.nsph
         split = os.environ.get("PC_GEN_COOP_SPLIT", "d")          # phase 2 by ket function d (default) or c
         if ND == 1:
             split = "c"
-        self.G = G = min(G, (ND if split == "d" else NC) if ket_split else G, ncart(lx1))
+        self.G = G = min(G, (ND if split == "d" else NC) if ket_split else G,
+                         sum(ncart(lx1 + k) for k in range(depth + 1)))
         self.nq = NC * ND
 
         def anc(e):
-            while sum(e) > lx1:
+            # chain of e: its ancestor `depth` levels above the bra shell (0: the lx1-level component)
+            while sum(e) > lx1 + depth:
                 e = dec(e, first_dir(e))
             return e
         chains = {}
@@ -981,6 +987,52 @@ class CoopGen:
         # roles are partial sums of the same elements: left in shared memory and reduced by the CTA
         self.defer = split == "d" and os.environ.get("PC_GEN_COOP_DEFER", "1") != "0"
         self.max_acc = max(len(es) for es in self.egroups) * base.nf
+
+    def regroup_by_cap(self, cap):
+        """Groups of bra components with at most `cap` accumulators each: the lx1-level chains,
+        those above the cap split into their next-level sub-chains, then merged greedily (largest
+        first) into the group whose recursion grows least."""
+        b = self.b
+        lx1 = b.l[0]
+        nf = b.nf
+
+        def anc(e, depth):
+            while sum(e) > lx1 + depth:
+                e = dec(e, first_dir(e))
+            return e
+        chains = {}
+        for e in b.e_list:
+            chains.setdefault((anc(e, 0),), []).append(e)
+        parts = []
+        for key, es in chains.items():
+            if len(es) * nf <= cap:
+                parts.append(es)
+                continue
+            subs = {}
+            for e in es:
+                subs.setdefault(anc(e, 1), []).append(e)      # the lx1-level component is its own key
+            root = subs.pop(key[0], [])
+            subl = sorted(subs.values(), key=len)
+            if subl:
+                subl[0] = root + subl[0]
+            else:
+                subl = [root]
+            parts.extend(subl)
+
+        def cost(es):
+            return sum(l.count("fma(") + l.count(" * ") for l in self.sub(es).gen_vrr())
+        bins = []
+        for es in sorted(parts, key=lambda x: -cost(x)):
+            fits = [k for k, bn in enumerate(bins) if (len(bn) + len(es)) * nf <= cap]
+            if fits:
+                k = min(fits, key=lambda k: cost(bins[k] + es) - cost(bins[k]))
+                bins[k] = bins[k] + es
+            else:
+                bins.append(list(es))
+        order = {e: k for k, e in enumerate(b.e_list)}
+        self.egroups = [sorted(bn, key=order.get) for bn in bins]
+        self.G = len(bins)
+        self.max_acc = max(len(es) for es in self.egroups) * nf
 
     def sub(self, es):
         g = ClassGen(*self.b.l)
@@ -1191,8 +1243,9 @@ class CoopGen:
 # classes built in the multi-pass form (ClassGenPass) and their number of passes: measured on
 # (H2O)32 (profiles/r2g_multipass_high_l.txt); (dd|ps), (pp|pp), (dp|ps) and (dd|dd) lose with it
 PASS_CLASSES = {"dppp": 2, "dpdp": 3, "dpds": 2, "ddds": 3, "ddpp": 4, "dddp": 6}
-if os.environ.get("PC_GEN_PASS") is not None:
-    PASS_CLASSES = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in os.environ["PC_GEN_PASS"].split(",") if kv and kv != "0")
+if os.environ.get("PC_GEN_PASS") is not None:       # name=passes or name=c<accumulator cap per pass>
+    PASS_CLASSES = dict((kv.split("=")[0], kv.split("=")[1] if kv.split("=")[1].startswith("c") else int(kv.split("=")[1]))
+                        for kv in os.environ["PC_GEN_PASS"].split(",") if kv and kv != "0")
 
 # classes built in the warp-cooperative form as well, and their number of roles
 COOP_CLASSES = {}
