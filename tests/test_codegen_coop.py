@@ -58,3 +58,32 @@ def test_generated_text(gen):
     assert "PYCHEM_B200_COOP" in src
     plain = gen.make_class((1, 1, 1, 0)).source()                    # a class outside PC_GEN_COOP is untouched
     assert "coop" not in plain
+
+
+def test_multi_pass_classes_partition_the_bra_components():
+    """ClassGenPass (the default form of six high-L classes): every bra component of the contracted
+    (e0|f0) belongs to exactly one pass, the kernel text has one pair of primitive loops per pass,
+    and the flop model is that of the one-pass class (the algorithmic count does not see passes)."""
+    sys.path.insert(0, os.path.join(HERE, "..", "pychem_b200", "codegen"))
+    try:
+        import gen_eri
+        gen_eri = importlib.reload(gen_eri)
+        assert set(gen_eri.PASS_CLASSES) == {"dppp", "dpdp", "dpds", "ddds", "ddpp", "dddp"}
+        for name, npass in gen_eri.PASS_CLASSES.items():
+            cls = tuple("spd".index(c) for c in name)
+            g = gen_eri.make_class(cls)
+            assert isinstance(g, gen_eri.ClassGenPass) and g.groups.G == npass
+            flat = [e for grp in g.groups.egroups for e in grp]
+            assert sorted(flat) == sorted(g.e_list) and len(set(flat)) == len(flat)
+            src = g.source()
+            assert src.count("for (int ik = 0; ik < KK;") == npass * len(gen_eri.MODES) // len(gen_eri.MODES)
+            plain = gen_eri.ClassGen(*cls)
+            plain.source_single()
+            assert gen_eri.flop_model(g) == gen_eri.flop_model(plain)
+        # Cartesian-d variants keep their forms
+        assert not isinstance(gen_eri.make_class((2, 1, 1, 1), cart_d=True), gen_eri.ClassGenPass)
+        # grouping by an accumulator cap: every pass within the cap
+        g = gen_eri.ClassGenPass(2, 2, 2, 1, npass="c112")
+        assert all(len(es) * g.nf <= 112 for es in g.groups.egroups) and g.groups.G == 5
+    finally:
+        sys.path.pop(0)
