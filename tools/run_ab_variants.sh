@@ -6,7 +6,7 @@
 # the first variant; with STEP=1 also the whole-build time of bench.py for each of them.
 O=gpurun_out/ab
 mkdir -p $O; rm -f $O/*
-timeout 1500 python tools/ab_classes.py --reps 3 --check $VARIANTS > $O/ab.jsonl 2> $O/ab.err; echo "ab rc=$?"
+timeout 1500 python tools/ab_classes.py --reps 3 ${CHECK---check} $VARIANTS > $O/ab.jsonl 2> $O/ab.err; echo "ab rc=$?"
 python - <<'PY'
 import json
 rows=[json.loads(l) for l in open('gpurun_out/ab/ab.jsonl')]
