@@ -664,13 +664,14 @@ class ClassGenPass(ClassGen):
 
             cart = {(ix, iy): hb(cx, cy) for ix, cx in enumerate(comps(lx1)) for iy, cy in enumerate(comps(ly1))}
             half = {}
+            cd = self.cart_d
             for ix in range(ncart(lx1)):
-                for my, row in enumerate(c2s_rows(ly1)):
+                for my, row in enumerate(c2s_rows_any(ly1, cd)):
                     half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
-            for mx, row in enumerate(c2s_rows(lx1)):
-                for my in range(nsph(ly1)):
+            for mx, row in enumerate(c2s_rows_any(lx1, cd)):
+                for my in range(nfun(ly1, cd)):
                     v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
-                    out.append("g[%d] = %s;" % ((mx * nsph(ly1) + my) * nq + q, v))
+                    out.append("g[%d] = %s;" % ((mx * nfun(ly1, cd) + my) * nq + q, v))
         for line in em.lines + out:
             s.append("  " + line)
 
@@ -1035,7 +1036,7 @@ class CoopGen:
         self.max_acc = max(len(es) for es in self.egroups) * nf
 
     def sub(self, es):
-        g = ClassGen(*self.b.l)
+        g = ClassGen(*self.b.l, cart_d=self.b.cart_d)
         g.e_list = list(es)
         g.ne = len(es)
         return g
@@ -1066,13 +1067,14 @@ class CoopGen:
 
             cart = {(ix, iy): hk(cx, cy) for ix, cx in enumerate(comps(lx2)) for iy, cy in enumerate(comps(ly2))}
             half = {}
+            cd = b.cart_d
             for ix in range(ncart(lx2)):
-                for my, row in enumerate(c2s_rows(ly2)):
+                for my, row in enumerate(c2s_rows_any(ly2, cd)):
                     half[(ix, my)] = lin_comb(em, [(c, cart[(ix, iy)]) for iy, c in row])
-            for mx, row in enumerate(c2s_rows(lx2)):
-                for my in range(nsph(ly2)):
+            for mx, row in enumerate(c2s_rows_any(lx2, cd)):
+                for my in range(nfun(ly2, cd)):
                     v = lin_comb(em, [(c, half[(ix, my)]) for ix, c in row])
-                    q = mx * nsph(ly2) + my
+                    q = mx * nfun(ly2, cd) + my
                     out.append("%s = %s;" % (dest % ((e_glob[e] * self.nq + q) * lane_stride), v))
         return em.lines + out
 
@@ -1287,8 +1289,8 @@ SKIP_CART = os.environ.get("PC_GEN_SKIP_CART", "0") != "0"
 
 def make_class(cls, cart_d=False):
     g = ClassGen(*cls, cart_d=cart_d)
-    if g.name in PASS_CLASSES and not g.cart_d:
-        return ClassGenPass(*cls, npass=PASS_CLASSES[g.name])
+    if g.name.lower() in PASS_CLASSES:        # the Cartesian-d variant (D in the name) of a class takes its form
+        return ClassGenPass(*cls, cart_d=cart_d, npass=PASS_CLASSES[g.name.lower()])
     g.gen_vrr()
     if g.n_vrr > V2_THRESHOLD:
         return ClassGenV2(*cls, cart_d=cart_d)

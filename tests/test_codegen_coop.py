@@ -80,8 +80,10 @@ def test_multi_pass_classes_partition_the_bra_components():
             plain = gen_eri.ClassGen(*cls)
             plain.source_single()
             assert gen_eri.flop_model(g) == gen_eri.flop_model(plain)
-        # Cartesian-d variants keep their forms
-        assert not isinstance(gen_eri.make_class((2, 1, 1, 1), cart_d=True), gen_eri.ClassGenPass)
+        # the Cartesian-d variant of a class takes the same form (six functions per d shell)
+        gc = gen_eri.make_class((2, 1, 1, 1), cart_d=True)
+        assert isinstance(gc, gen_eri.ClassGenPass) and gc.name == "Dppp" and gc.nsph == [6, 3, 3, 3]
+        assert "g[%d]" % (6 * 3 * 3 * 3 - 1) in gc.source()
         # grouping by an accumulator cap: every pass within the cap
         g = gen_eri.ClassGenPass(2, 2, 2, 1, npass="c112")
         assert all(len(es) * g.nf <= 112 for es in g.groups.egroups) and g.groups.G == 5
