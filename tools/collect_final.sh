@@ -10,7 +10,7 @@ for c in psss psps ppps; do
   python tools/ncu_raw_summary.py $F/${c}2_raw.csv >> $P/r2_final_ncu_full_psss_psps_ppps_jk.txt
   python tools/ncu_regions.py $F/src_${c}_mode2.csv.gz > $P/r2_final_stalls_${c}_jk.txt 2>/dev/null || python tools/ncu_top_stalls.py $F/src_${c}_mode2.csv.gz > $P/r2_final_stalls_${c}_jk.txt
 done
-extra=""; [ -f gpurun_out/hiL/dppp2_raw.csv ] && extra="gpurun_out/hiL/dppp2_raw.csv gpurun_out/hiL/dpdp2_raw.csv gpurun_out/hiL/ddpp2_raw.csv"
+extra=""; for f in gpurun_out/hiL/dppp2_raw.csv gpurun_out/hiL/dpdp2_raw.csv gpurun_out/hiL/ddpp2_raw.csv; do [ -f $f ] && extra="$extra $f"; done
 python tools/ncu_traffic_json.py $P/ncu_traffic.json "ncu --set full --clock-control none, round 2" $F/psss2_raw.csv $F/psps2_raw.csv $F/ppps2_raw.csv $extra
 tail -2 $F/tests.log > $P/r2_final_gpu_tests.txt
 ls -la $P/r2_final_*
