@@ -16,6 +16,13 @@ pair-class(bra) >= pair-class(ket) this writes pychem_b200/csrc/gen/eri_<class>.
 
 The recursion DAG that the reference rebuilds in Python for every shell quartet
 (integrals.SetRR2, integrals.py:73-191) is resolved here once, at code-generation time.
+
+Kernel forms (make_class picks one per class): ClassGen -- straight-line, one quartet per thread
+(`source_single`) or one ket pair x a run of bra pairs per thread (`source_run`, RUN_CLASSES);
+ClassGenPass -- the primitive loops once per group of bra components, accumulators in registers
+(PASS_CLASSES: the six classes whose contracted block does not fit the registers);
+ClassGenV2 -- rolled loops for (dd|dd).  CoopGen (PC_GEN_COOP) is the measured-and-shelved
+warp-cooperative variant of the same decomposition as ClassGenPass.
 """
 import math
 import os

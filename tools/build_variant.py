@@ -27,7 +27,7 @@ def main():
         emu = True
         args = args[1:]
     name, env = args[0], dict(a.split("=", 1) for a in args[1:])
-    nvcc_extra = env.pop("NVCC", "").split()          # e.g. NVCC="-DPC_ABL_NO_RED -DPC_BOYS_LDG256=1"
+    nvcc_extra = env.pop("NVCC", "").split()          # e.g. NVCC="-DPC_ABL_NO_RED -DPC_BOYS_COMPACT_MINL=2"
     if not emu:
         env.setdefault("PC_GEN_SKIP_CART", "1")       # timing variants: spherical kernels only
         env.setdefault("PC_GEN_MODES", "0,2,5")       # ... in the modes the A/B harness runs
